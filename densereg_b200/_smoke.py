@@ -1,0 +1,40 @@
+"""smoke(): one tiny invocation of the hot path on cuda:0, checked against the CPU oracle
+(forward + vote, and one training micro-step)."""
+import numpy as np
+import torch
+
+
+def run():
+    from .engine import DenseRegEngine
+    from . import synth
+    from oracle import um_v1_torch as U, vote_numpy as V   # checker only
+    S, F, J, B = 1, 64, 16, 2
+    eng = DenseRegEngine(S, F, J, max_batch=B, training=True)
+    net = U.Net(S, F, J)
+    p, s = net.init_params(0, stddev=0.05), net.init_state()
+    eng.load_flat(p, s)
+    dms, poses, cfgs, coms = synth.make_batch(B, J, seed=1)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    d, po, cf, co = cu(dms), cu(poses), cu(cfgs), cu(coms)
+    # inference: crops -> xyz mm
+    xyz = eng.infer(d, cf, co).cpu().numpy()
+    x0n = V.norm_dm(dms[..., 0], coms)
+    hms, hm3s, ums = net.forward(p, s, torch.from_numpy(x0n[..., None]), training=False)
+    out = eng.forward(d, co)
+    e_map = float((out["um_outs"][-1].cpu() - ums[-1]).abs().max() / ums[-1].abs().max())
+    # vote on the GPU's own maps vs oracle vote on the same maps: indices exact, xyz <= 1e-3 mm
+    hm_g, hm3_g, um_g = (out[k][-1].cpu().numpy() for k in ("hm_outs", "hm3_outs", "um_outs"))
+    ref_xyz, ref_top5 = V.xyz_estimation(hm_g, hm3_g, um_g, V.tiny_dm(x0n), cfgs, coms)
+    ok = np.isfinite(ref_xyz)
+    e_xyz = float(np.abs(xyz - ref_xyz)[ok].max())
+    # one training micro-step
+    eng.zero_grads()
+    loss = eng.loss_backward(d, po, cf, co, dropout_seed=3).cpu().numpy()
+    L, g_ref, _ = U.loss_and_grads(net, p, s.clone(), dms[..., 0], poses, cfgs, coms, dropout_seed=3)
+    e_loss = abs(loss[0] - L["total"]) / abs(L["total"])
+    e_grad = float((eng.grads.cpu() - g_ref).norm() / g_ref.norm())
+    eng.optimizer_step(step=1, lr=1e-3)
+    torch.cuda.synchronize()
+    print("smoke: map relerr %.2e | vote xyz err %.2e mm | loss relerr %.2e | grad relerr %.2e | launches %d"
+          % (e_map, e_xyz, e_loss, e_grad, eng.launch_count))
+    assert e_map < 1e-4 and e_xyz <= 1e-3 and e_loss < 1e-4 and e_grad < 1e-3

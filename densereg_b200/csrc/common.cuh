@@ -1,0 +1,109 @@
+// common.cuh -- shared declarations for libdensereg_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define DR_DEVINL __device__ __forceinline__
+
+// counter-based keep/drop decision for dropout (keep prob 0.5, network/slim/ops.py:711).
+// Same splitmix64 finaliser as oracle/um_v1_torch.py:dropout_mask so masks are reproducible.
+__host__ __device__ inline uint32_t dr_hash_keep(uint64_t seed, uint32_t tag, uint64_t i) {
+  uint64_t x = i + seed * 0x9E3779B97F4A7C15ull + (uint64_t)tag * 0xD1B54A32D192ED03ull;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 63);
+}
+
+// ---- conv problem description shared by the SIMT and tcgen05 paths --------------------------
+struct ConvProblem {
+  // input activation view: element (b,y,x,c) at x[((b*H + y)*W + x)*x_cs + c]
+  const float* x; int x_cs;
+  int B, H, W, Cin;
+  int Ho, Wo, Cout;
+  int k, stride, pad_t, pad_l;
+  const float* w;          // [k*k*Cin][Cout] row-major (TF HWIO flattened)
+  float* y; int y_cs;      // output view
+  // epilogue: v = acc*scale[n] + shift[n]; relu; dropout; + res; + beta*y_old
+  const float* scale;      // may be null (=1)
+  const float* shift;      // may be null (=0)
+  int relu;
+  const float* res; int res_cs;   // residual view at output resolution (may be null)
+  int accumulate;          // y = v + y_old
+  int dropout;             // apply keep/2x after relu
+  uint64_t drop_seed; uint32_t drop_tag;
+};
+
+struct WgradProblem {
+  const float* x; int x_cs;       // forward input view (B,H,W,Cin)
+  const float* dy; int dy_cs;     // grad of raw conv output (B,Ho,Wo,Cout)
+  int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad_t, pad_l;
+  float* dw;                      // [k*k*Cin][Cout], ACCUMULATED with atomics
+};
+
+// launchers (each returns the number of kernels launched)
+int launch_conv_simt(const ConvProblem& p, cudaStream_t st);
+int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st);
+
+// tcgen05 path (conv_tc.cu). Returns 0 launches if the problem shape is not eligible.
+bool conv_tc_eligible(const ConvProblem& p);
+int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st);
+
+// ---- vote -----------------------------------------------------------------------------------
+int launch_vote(int B, int H, int W, int J,
+                const float* hm, int hm_cs, const float* hm3, int hm3_cs, const float* um, int um_cs,
+                const float* dm, const float* cfgs, const float* coms,
+                float* xyz, int32_t* top5, int32_t* clamp_count, cudaStream_t st);
+
+// ---- elementwise / reductions (ew.cu) ---------------------------------------------------------
+int launch_norm_dm(int B, int hw, const float* dm, const float* coms, float* out, cudaStream_t st);
+// writes uu,vv,tiny_dm (3 channels) for every 32x32 pixel into up to 8 destination views
+struct UvdDst { float* p[8]; int cs[8]; int n; };
+int launch_make_uvd(int B, int in_hw, int out_hw, const float* x0, float* tiny, UvdDst dst, cudaStream_t st);
+int launch_maxpool(int B, int H, int W, int C, int k, const float* x, int x_cs, float* y, int y_cs, cudaStream_t st);
+int launch_maxpool_bwd(int B, int H, int W, int C, int k, const float* x, int x_cs, const float* dy, int dy_cs,
+                       float* dx, int dx_cs, int accumulate, cudaStream_t st);
+int launch_upadd(int B, int H, int W, int C, const float* a, int a_cs, const float* lo, int lo_cs, float* y, int y_cs, cudaStream_t st);
+// dlo (H/2,W/2) (+)= 2x2 sum of dy
+int launch_upadd_bwd_lo(int B, int H, int W, int C, const float* dy, int dy_cs, float* dlo, int dlo_cs, int accumulate, cudaStream_t st);
+// dst (+)= src (views, same shape); optional depth mask (zero where tiny<-0.9)
+int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* dst, int dst_cs, int accumulate,
+                     const float* tiny_mask, cudaStream_t st);
+int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st);
+int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums /*2C, pre-zeroed*/, cudaStream_t st);
+// BRN finalize (train): sums -> mean/var, r, d, affine a,b; optional state update. bstat: mean,inv_std,r,d [C each]
+int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
+                        float* aff, float* bstat, int update_state, cudaStream_t st);
+// eval fold: aff = {scale, shift} from moving stats (or {1,bias})
+int launch_fold_affine(int C, int brn, const float* pbeta_gamma_or_bias, const float* state, float* aff, cudaStream_t st);
+// y = act(raw*a+b) (+res)
+int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
+                     const float* res, int res_cs, float* y, int y_cs, cudaStream_t st);
+// backward reductions: g = dy*(z>0); sums[0:C]=sum g, sums[C:2C]=sum g*xhat   (z = raw*a+b, xhat=(raw-mean)*inv_std)
+int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
+                          const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st);
+// draw = gamma*r*inv_std*(g - sum_g/N - xhat*sum_gx/N); also dbeta,dgamma accumulated into gparam
+int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
+                         const float* aff, const float* bstat, const float* beta_gamma, int relu,
+                         const double* sums, float* draw, int draw_cs, float* gparam, cudaStream_t st);
+// bias conv backward: dz = dy * (relu? (out>0)*(dropout?2:1) : 1); dbias accumulated
+int launch_bias_bwd(size_t npix, int C, const float* dy, int dy_cs, const float* out, int out_cs, int relu, int dropout,
+                    float* dz, int dz_cs, float* gbias, cudaStream_t st);
+// loss + GT synthesis + output grads for all stacks
+struct LossArgs {
+  int B, hw, J, S;
+  const float* tiny;          // (B,hw,hw) normalised depth
+  const float* poses; const float* cfgs; const float* coms;
+  const float* hm[4]; const float* hm3[4]; const float* um[4]; int cs[4];
+  float* ghm[4]; float* ghm3[4]; float* gum[4]; int gcs[4];
+  double* loss_acc;           // 3 doubles (hm, hm3, um), pre-zeroed
+};
+int launch_loss(const LossArgs& a, cudaStream_t st);
+int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, double* reg_acc, cudaStream_t st);
+int launch_finish_loss(const double* acc /*hm,hm3,um,reg*/, float* out5, cudaStream_t st);
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
+                float lr_t, float b1, float b2, float eps, cudaStream_t st);
+int launch_transpose_weights(int k, int cin, int cout, const float* w, float* wt, cudaStream_t st);
+int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st);
+int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, float* dst, cudaStream_t st);

@@ -1,0 +1,753 @@
+// engine.cu -- graph construction, forward / backward schedules and the C-ABI of
+// libdensereg_sm100.so (include/densereg.h).
+//
+// The graph is built once per handle by walking network/um_v1.py:detect_net (:71-185) in TF variable-
+// creation order; tensors are NHWC fp32 "views" into one activation arena so every tf.concat on the
+// path is a channel-offset write.  Backward is an explicit reverse schedule (no tape): BRN backward
+// -> dgrad (the forward conv kernel with rotated/transposed weights) -> wgrad, with a build-time
+// tracker deciding overwrite-vs-accumulate for every gradient write.
+#include "../../include/densereg.h"
+#include "common.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Layer {
+  char name[48];
+  int k, stride, cin, cout, brn, relu;
+  float wd;
+  int64_t w_off, p_off, s_off;
+  int64_t aff_off, bstat_off, sum_off;
+  int in_hw, out_hw;
+};
+
+struct LayerDev { int C, brn, kk, cin; long long w_off, p_off, s_off, aff_off; };
+
+struct Buf { int H, W, C, Cs; size_t off; int raw; };   // Cs = padded channel stride; off in per-crop elements
+struct View { int buf = -1; int coff = 0; int C = 0; };
+
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UPADD = 2, OP_MASKCOPY = 3 };
+
+struct GradWrite { int acc = 0; int nfill = 0; View fill[4]; };
+
+struct Op {
+  OpKind kind;
+  int layer = -1;
+  View in, out, res;
+  int raw = -1;
+  int accumulate = 0;
+  int dropout_tag = -1;
+  int k = 0;
+  int need_dgrad = 1;
+  GradWrite gw_in, gw_res;
+};
+
+}  // namespace
+
+struct dr_handle {
+  dr_config cfg;
+  std::vector<Layer> layers;
+  std::vector<Buf> bufs;
+  std::vector<Op> ops;
+  size_t n_params = 0, n_state = 0, n_aff = 0, n_bstat = 0, n_sums = 0;
+  size_t act_per_crop = 0, raw_per_crop = 0, scratch_per_crop = 0;
+  int buf_x0 = -1, buf_tiny = -1;
+  std::vector<View> uvd_dst;
+  View hg_ins0;
+  std::vector<View> v_hm, v_hm3, v_um;
+  // bound buffers
+  float *params = nullptr, *state = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  // owned device memory
+  float *act = nullptr, *gact = nullptr, *rawa = nullptr, *scratch = nullptr;
+  float *aff = nullptr, *bstat = nullptr, *wt = nullptr, *wdmask = nullptr;
+  double *sums = nullptr, *sums_bw = nullptr, *loss_acc = nullptr;
+  int32_t* clamp_dev = nullptr;
+  LayerDev* ltab = nullptr;
+  int cap_B = 0; bool cap_train = false;
+  size_t ws_bytes = 0;
+  int64_t launches = 0;
+  std::string err;
+  int precision = 0;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                  \
+      return DR_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+inline int fail(dr_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+int same_pad_before(int n, int k, int s) {
+  int out = (n + s - 1) / s;
+  int total = (out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph builder
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+  dr_handle* h;
+  int F, J, S;
+  int new_buf(int hw, int C, int raw = 0) {
+    Buf b; b.H = hw; b.W = hw; b.C = C; b.Cs = (C + 3) / 4 * 4; b.raw = raw;
+    size_t& total = raw ? h->raw_per_crop : h->act_per_crop;
+    b.off = total; total += (size_t)hw * hw * b.Cs;
+    h->bufs.push_back(b);
+    return (int)h->bufs.size() - 1;
+  }
+  View V(int buf) { View v; v.buf = buf; v.coff = 0; v.C = h->bufs[buf].C; return v; }
+  View sub(int buf, int coff, int C) { View v; v.buf = buf; v.coff = coff; v.C = C; return v; }
+  int add_layer(const std::string& name, int k, int stride, int cin, int cout, int brn, int relu, float wd, int in_hw) {
+    Layer L; memset(&L, 0, sizeof(L));
+    snprintf(L.name, sizeof(L.name), "%s", name.c_str());
+    L.k = k; L.stride = stride; L.cin = cin; L.cout = cout; L.brn = brn; L.relu = relu; L.wd = wd;
+    L.in_hw = in_hw; L.out_hw = (in_hw + stride - 1) / stride;
+    L.w_off = (int64_t)h->n_params; h->n_params += (size_t)k * k * cin * cout;
+    L.p_off = (int64_t)h->n_params; h->n_params += brn ? 2 * cout : cout;
+    L.s_off = (int64_t)h->n_state; if (brn) h->n_state += 4 * cout + 4;
+    L.aff_off = (int64_t)h->n_aff; h->n_aff += 2 * cout;
+    L.bstat_off = (int64_t)h->n_bstat; h->n_bstat += 4 * cout;
+    L.sum_off = (int64_t)h->n_sums; h->n_sums += 2 * cout;
+    h->layers.push_back(L);
+    return (int)h->layers.size() - 1;
+  }
+  void conv_op(int layer, View in, View out, View res = View(), int accumulate = 0, int dropout_tag = -1) {
+    Op o; o.kind = OP_CONV; o.layer = layer; o.in = in; o.out = out; o.res = res;
+    o.accumulate = accumulate; o.dropout_tag = dropout_tag;
+    const Layer& L = h->layers[layer];
+    if (L.brn) o.raw = new_buf(L.out_hw, L.cout, 1);
+    size_t sc = (size_t)L.out_hw * L.out_hw * ((L.cout + 3) / 4 * 4);
+    if (sc > h->scratch_per_crop) h->scratch_per_crop = sc;
+    h->ops.push_back(o);
+  }
+  void residual(const std::string& name, View in, int cin, int cout, View dest, int hw) {
+    int hc = cin / 2;
+    int L1 = add_layer(name + "/c1", 1, 1, cin, hc, 1, 1, 0.0005f, hw);
+    int L2 = add_layer(name + "/c2", 3, 1, hc, hc, 1, 1, 0.0005f, hw);
+    int L3 = add_layer(name + "/c3", 1, 1, hc, cout, 1, 1, 0.0005f, hw);
+    int Ls = cout != cin ? add_layer(name + "/skip", 1, 1, cin, cout, 1, 1, 0.0005f, hw) : -1;
+    int t1 = new_buf(hw, hc), t2 = new_buf(hw, hc);
+    conv_op(L1, in, V(t1));
+    conv_op(L2, V(t1), V(t2));
+    View sk = in;
+    if (Ls >= 0) { int sb = new_buf(hw, cout); conv_op(Ls, in, V(sb)); sk = V(sb); }
+    conv_op(L3, V(t2), dest, sk);
+  }
+  void hourglass(const std::string& name, int n, View x, View dest, int hw) {
+    char tag[16]; snprintf(tag, sizeof(tag), "/n%d", n);
+    std::string p = name + tag;
+    int up1 = new_buf(hw, F);
+    residual(p + "/upper1", x, F, F, V(up1), hw);
+    int pl = new_buf(hw / 2, F);
+    { Op o; o.kind = OP_POOL; o.in = x; o.out = V(pl); o.k = 3; h->ops.push_back(o); }
+    int low1 = new_buf(hw / 2, F);
+    residual(p + "/lower1", V(pl), F, F, V(low1), hw / 2);
+    int low2 = low1;
+    if (n > 1) { low2 = new_buf(hw / 2, F); hourglass(name, n - 1, V(low1), V(low2), hw / 2); }
+    int low3 = new_buf(hw / 2, F);
+    residual(p + "/lower3", V(low2), F, F, V(low3), hw / 2);
+    { Op o; o.kind = OP_UPADD; o.in = V(up1); o.res = V(low3); o.out = dest; h->ops.push_back(o); }
+  }
+  void build() {
+    F = h->cfg.num_fea; J = h->cfg.num_jnt; S = h->cfg.num_stack;
+    const int IN = h->cfg.in_hw, OUT = h->cfg.out_hw;
+    h->buf_x0 = new_buf(IN, 1);
+    h->buf_tiny = new_buf(OUT, 1);
+    // stem: um_v1.py:84-97
+    int Lc1 = add_layer("stem/conv_1", 7, 2, 1, 32, 1, 1, 0.0005f, IN);
+    int c1 = new_buf(IN / 2, 32);
+    conv_op(Lc1, V(h->buf_x0), V(c1));
+    h->ops.back().need_dgrad = 0;
+    int c2 = new_buf(IN / 2, 64);
+    residual("stem/conv_2", V(c1), 32, 64, V(c2), IN / 2);
+    int p1 = new_buf(OUT, 64);
+    { Op o; o.kind = OP_POOL; o.in = V(c2); o.out = V(p1); o.k = 2; h->ops.push_back(o); }
+    int c3 = new_buf(OUT, 64);
+    residual("stem/conv_3", V(p1), 64, 64, V(c3), OUT);
+    int c4 = new_buf(OUT, F);
+    residual("stem/conv_4", V(c3), 64, F, V(c4), OUT);
+    View hg_ins = V(c4);
+    h->hg_ins0 = hg_ins;
+    for (int s = 0; s < S; ++s) {
+      char ps[16]; snprintf(ps, sizeof(ps), "s%d", s);
+      std::string p = ps;
+      int big = new_buf(OUT, F + 5 * J);
+      View hg_outs = sub(big, 0, F), hm = sub(big, F, J), hm3 = sub(big, F + J, J), um = sub(big, F + 2 * J, 3 * J);
+      View cat = sub(big, 0, F + 2 * J), tmp_out = sub(big, F, 5 * J);
+      h->v_hm.push_back(hm); h->v_hm3.push_back(hm3); h->v_um.push_back(um);
+      hourglass(p + "/hg", 4, hg_ins, hg_outs, OUT);                         // um_v1.py:125
+      int llr = new_buf(OUT, F);
+      residual(p + "/ll_res", hg_outs, F, F, V(llr), OUT);                   // :127
+      int lluvd = new_buf(OUT, F + 3);
+      View ll = sub(lluvd, 0, F);
+      h->uvd_dst.push_back(sub(lluvd, F, 3));
+      conv_op(add_layer(p + "/ll", 1, 1, F, F, 1, 1, 0.0005f, OUT), V(llr), ll);              // :128-131
+      conv_op(add_layer(p + "/hm_out", 1, 1, F, J, 0, 0, 0.0005f, OUT), ll, hm);               // :133-135
+      int h3 = new_buf(OUT, 128);
+      residual(p + "/hm3_res", V(lluvd), F + 3, 128, V(h3), OUT);            // :137-138
+      conv_op(add_layer(p + "/hm3_out", 1, 1, 128, J, 0, 0, 0.0005f, OUT), V(h3), hm3);        // :139-141
+      int u1 = new_buf(OUT, 256);
+      residual(p + "/um_res1", cat, F + 2 * J, 256, V(u1), OUT);             // :143-144
+      int combin = new_buf(OUT, 512);
+      residual(p + "/um_res2", V(u1), 256, 256, sub(combin, 0, 256), OUT);
+      int catm = new_buf(OUT, F + 2 * J);
+      { Op o; o.kind = OP_MASKCOPY; o.in = cat; o.out = V(catm); h->ops.push_back(o); }      // :146-148
+      int m1 = new_buf(OUT, 256);
+      residual(p + "/um_mask_res1", V(catm), F + 2 * J, 256, V(m1), OUT);    // :149
+      residual(p + "/um_mask_res2", V(m1), 256, 256, sub(combin, 256, 256), OUT);
+      int combuvd = new_buf(OUT, 515);
+      residual(p + "/um_comb", V(combin), 512, 512, sub(combuvd, 0, 512), OUT);   // :151-152
+      h->uvd_dst.push_back(sub(combuvd, 512, 3));                              // :153
+      int f1 = new_buf(OUT, 512), f2 = new_buf(OUT, 512);
+      conv_op(add_layer(p + "/um_full1", 1, 1, 515, 512, 0, 1, 0.0005f, OUT), V(combuvd), V(f1), View(), 0, 2 * s);      // :155-159
+      conv_op(add_layer(p + "/um_full2", 1, 1, 512, 512, 0, 1, 0.0005f, OUT), V(f1), V(f2), View(), 0, 2 * s + 1);    // :160-164
+      conv_op(add_layer(p + "/um_out", 1, 1, 512, 3 * J, 0, 0, 0.0005f, OUT), V(f2), um);                              // :166-169
+      if (s < S - 1) {                                                          // :174-183
+        int nxt = new_buf(OUT, F);
+        conv_op(add_layer(p + "/inter_out", 1, 1, 5 * J, F, 0, 0, 0.f, OUT), tmp_out, V(nxt), hg_ins);
+        conv_op(add_layer(p + "/inter_ll", 1, 1, F, F, 0, 0, 0.f, OUT), ll, V(nxt), View(), 1);
+        hg_ins = V(nxt);
+      }
+    }
+    plan_backward();
+  }
+
+  // decide overwrite / accumulate for each gradient write of the reverse schedule
+  void plan_backward() {
+    std::vector<std::vector<char>> written(h->bufs.size());
+    for (size_t i = 0; i < h->bufs.size(); ++i) written[i].assign(h->bufs[i].Cs, 0);
+    auto mark = [&](const View& v) { for (int c = 0; c < v.C; ++c) written[v.buf][v.coff + c] = 1; };
+    auto plan = [&](const View& v) {
+      GradWrite g;
+      int nw = 0;
+      for (int c = 0; c < v.C; ++c) nw += written[v.buf][v.coff + c];
+      if (nw == 0) { g.acc = 0; }
+      else if (nw == v.C) { g.acc = 1; }
+      else {
+        g.acc = 1;
+        int c = 0;
+        while (c < v.C) {
+          if (written[v.buf][v.coff + c]) { ++c; continue; }
+          int c0 = c;
+          while (c < v.C && !written[v.buf][v.coff + c]) ++c;
+          if (g.nfill < 4) { View f; f.buf = v.buf; f.coff = v.coff + c0; f.C = c - c0; g.fill[g.nfill++] = f; }
+        }
+      }
+      mark(v);
+      return g;
+    };
+    for (size_t s = 0; s < h->v_hm.size(); ++s) { mark(h->v_hm[s]); mark(h->v_hm3[s]); mark(h->v_um[s]); }   // loss kernel
+    for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
+      Op& o = h->ops[i];
+      switch (o.kind) {
+        case OP_CONV:
+          if (o.res.buf >= 0) o.gw_res = plan(o.res);
+          if (o.need_dgrad) o.gw_in = plan(o.in);
+          break;
+        case OP_POOL: o.gw_in = plan(o.in); break;
+        case OP_UPADD: o.gw_in = plan(o.in); o.gw_res = plan(o.res); break;
+        case OP_MASKCOPY: o.gw_in = plan(o.in); break;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// table-driven helper kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_all_kernel(const LayerDev* __restrict__ t, const float* __restrict__ params, const float* __restrict__ state,
+                                float* __restrict__ aff) {
+  const LayerDev L = t[blockIdx.x];
+  const float* pb = params + L.p_off;
+  float* a = aff + L.aff_off;
+  for (int c = threadIdx.x; c < L.C; c += blockDim.x) {
+    if (L.brn) {                                           // network/slim/ops.py:173-180
+      const float* st = state + L.s_off;
+      float inv = (1.0f / sqrtf(st[L.C + c] + 0.001f)) * pb[L.C + c];
+      a[c] = inv; a[L.C + c] = pb[c] - st[c] * inv;
+    } else {
+      a[c] = 1.0f; a[L.C + c] = pb[c];
+    }
+  }
+}
+
+// wt[(kk-1-tap)][n][c] = w[tap][c][n] for every layer (dgrad weights)
+__global__ void transpose_all_kernel(const LayerDev* __restrict__ t, const float* __restrict__ params, float* __restrict__ wt) {
+  const LayerDev L = t[blockIdx.x];
+  const float* w = params + L.w_off;
+  float* o = wt + L.w_off;
+  const size_t n = (size_t)L.kk * L.cin * L.C;
+  for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) {
+    int c = (int)(i % L.cin); size_t r = i / L.cin; int n_o = (int)(r % L.C); int tap = (int)(r / L.C);
+    o[i] = w[((size_t)(L.kk - 1 - tap) * L.cin + c) * L.C + n_o];
+  }
+}
+
+__global__ void init_state_kernel(const LayerDev* __restrict__ t, float* __restrict__ params, float* __restrict__ state) {
+  const LayerDev L = t[blockIdx.x];
+  float* pb = params + L.p_off;
+  for (int c = threadIdx.x; c < L.C; c += blockDim.x) {
+    pb[c] = 0.f;                                           // beta / biases = 0
+    if (L.brn) {
+      pb[L.C + c] = 1.f;                                   // gamma = 1
+      float* st = state + L.s_off;
+      st[c] = 0.f; st[L.C + c] = 1.f; st[2 * L.C + c] = 0.f; st[3 * L.C + c] = 0.f;
+    }
+  }
+  if (L.brn && threadIdx.x == 0) {
+    float* st = state + L.s_off + 4 * L.C;
+    st[0] = 1.f; st[1] = 0.f; st[2] = 0.f; st[3] = 0.f;    // r_max, d_max, curr_t, local_step
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution helpers
+// ---------------------------------------------------------------------------------------------
+struct Exec {
+  dr_handle* h; int B; cudaStream_t st;
+  float* ptr(const View& v) const {
+    const Buf& b = h->bufs[v.buf];
+    float* base = b.raw ? h->rawa : h->act;
+    return base + b.off * h->cap_B + v.coff;
+  }
+  float* gptr(const View& v) const {
+    const Buf& b = h->bufs[v.buf];
+    return h->gact + b.off * h->cap_B + v.coff;
+  }
+  int cs(const View& v) const { return h->bufs[v.buf].Cs; }
+  size_t npix(const View& v) const { const Buf& b = h->bufs[v.buf]; return (size_t)B * b.H * b.W; }
+  View whole(int buf) const { View v; v.buf = buf; v.coff = 0; v.C = h->bufs[buf].C; return v; }
+};
+
+int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
+  if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) return launch_conv_tc(p, precision == DR_PREC_TF32X3, st);
+  return launch_conv_simt(p, st);
+}
+
+int ensure_workspace(dr_handle* h, int B, bool train) {
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, DR_ERR_ARG, "batch exceeds dr_config.max_batch");
+  if (h->cap_B >= h->cfg.max_batch && (h->cap_train || !train)) return DR_OK;
+  const int cap = h->cfg.max_batch;
+  if (!h->act) {
+    size_t bytes = h->act_per_crop * cap * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->act, bytes)); h->ws_bytes += bytes;
+    CUDA_TRY(h, cudaMemset(h->act, 0, bytes));
+  }
+  if (train && !h->cap_train) {
+    size_t bytes = h->act_per_crop * cap * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->gact, bytes)); h->ws_bytes += bytes;
+    CUDA_TRY(h, cudaMemset(h->gact, 0, bytes));
+    bytes = h->raw_per_crop * cap * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->rawa, bytes)); h->ws_bytes += bytes;
+    bytes = h->scratch_per_crop * cap * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->scratch, bytes)); h->ws_bytes += bytes;
+    bytes = h->n_params * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->wt, bytes)); h->ws_bytes += bytes;
+    h->cap_train = true;
+  }
+  h->cap_B = cap;
+  return DR_OK;
+}
+
+int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int training, int update_state,
+                 uint64_t dropout_seed, cudaStream_t st) {
+  if (!h->params || !h->state) return fail(h, DR_ERR_STATE, "dr_bind() not called");
+  int rc = ensure_workspace(h, B, training != 0);
+  if (rc) return rc;
+  Exec X{h, B, st};
+  const int IN = h->cfg.in_hw, OUT = h->cfg.out_hw;
+  int nl = 0;
+  // norm_dm + uvd / tiny_dm
+  float* x0 = X.ptr(X.whole(h->buf_x0));
+  float* tiny = X.ptr(X.whole(h->buf_tiny));
+  nl += launch_norm_dm(B, IN, dm_mm, coms, x0, st);
+  UvdDst ud; ud.n = (int)h->uvd_dst.size();
+  if (ud.n > 8) return fail(h, DR_ERR_UNSUPPORTED, "num_stack > 4 not supported");
+  for (int i = 0; i < ud.n; ++i) { ud.p[i] = X.ptr(h->uvd_dst[i]); ud.cs[i] = X.cs(h->uvd_dst[i]); }
+  nl += launch_make_uvd(B, IN, OUT, x0, tiny, ud, st);
+  if (training) {
+    CUDA_TRY(h, cudaMemsetAsync(h->sums, 0, h->n_sums * sizeof(double), st));
+  } else {
+    fold_all_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state, h->aff); ++nl;
+  }
+  for (size_t oi = 0; oi < h->ops.size(); ++oi) {
+    const Op& o = h->ops[oi];
+    switch (o.kind) {
+      case OP_CONV: {
+        const Layer& L = h->layers[o.layer];
+        ConvProblem p; memset(&p, 0, sizeof(p));
+        p.x = X.ptr(o.in); p.x_cs = X.cs(o.in);
+        p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
+        p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
+        p.w = h->params + L.w_off;
+        const float* aff = h->aff + L.aff_off;
+        const float* res = o.res.buf >= 0 ? X.ptr(o.res) : nullptr;
+        const int res_cs = o.res.buf >= 0 ? X.cs(o.res) : 0;
+        if (training && L.brn) {
+          View rv = X.whole(o.raw);
+          p.y = X.ptr(rv); p.y_cs = X.cs(rv);
+          nl += run_conv(h, p, h->precision, st);
+          double* sums = h->sums + L.sum_off;
+          nl += launch_channel_stats(X.npix(rv), L.cout, p.y, p.y_cs, sums, st);
+          nl += launch_brn_finalize(L.cout, (double)X.npix(rv), sums, h->params + L.p_off, h->state + L.s_off,
+                                    h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
+          nl += launch_brn_apply(X.npix(rv), L.cout, p.y, p.y_cs, aff, L.relu, res, res_cs, X.ptr(o.out), X.cs(o.out), st);
+        } else {
+          p.y = X.ptr(o.out); p.y_cs = X.cs(o.out);
+          if (L.brn) { p.scale = aff; p.shift = aff + L.cout; }
+          else { p.scale = nullptr; p.shift = h->params + L.p_off; }
+          p.relu = L.relu; p.res = res; p.res_cs = res_cs; p.accumulate = o.accumulate;
+          if (training && o.dropout_tag >= 0) { p.dropout = 1; p.drop_seed = dropout_seed; p.drop_tag = (uint32_t)o.dropout_tag; }
+          nl += run_conv(h, p, h->precision, st);
+        }
+        break;
+      }
+      case OP_POOL: {
+        const Buf& bi = h->bufs[o.in.buf];
+        nl += launch_maxpool(B, bi.H, bi.W, o.in.C, o.k, X.ptr(o.in), X.cs(o.in), X.ptr(o.out), X.cs(o.out), st);
+        break;
+      }
+      case OP_UPADD: {
+        const Buf& bo = h->bufs[o.out.buf];
+        nl += launch_upadd(B, bo.H, bo.W, o.out.C, X.ptr(o.in), X.cs(o.in), X.ptr(o.res), X.cs(o.res), X.ptr(o.out), X.cs(o.out), st);
+        break;
+      }
+      case OP_MASKCOPY:
+        nl += launch_copy_view(X.npix(o.in), o.in.C, X.ptr(o.in), X.cs(o.in), X.ptr(o.out), X.cs(o.out), 0, tiny, st);
+        break;
+    }
+  }
+  h->launches += nl;
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int apply_fills(dr_handle* h, Exec& X, const GradWrite& g, cudaStream_t st) {
+  int nl = 0;
+  for (int i = 0; i < g.nfill; ++i) nl += launch_fill_view(X.npix(g.fill[i]), g.fill[i].C, X.gptr(g.fill[i]), X.cs(g.fill[i]), 0.f, st);
+  return nl;
+}
+
+int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, const float* coms, float* loss_out, cudaStream_t st) {
+  if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
+  Exec X{h, B, st};
+  int nl = 0;
+  const int OUT = h->cfg.out_hw, J = h->cfg.num_jnt, S = h->cfg.num_stack;
+  CUDA_TRY(h, cudaMemsetAsync(h->sums_bw, 0, h->n_sums * sizeof(double), st));
+  CUDA_TRY(h, cudaMemsetAsync(h->loss_acc, 0, 4 * sizeof(double), st));
+  transpose_all_kernel<<<dim3((unsigned)h->layers.size(), 8), 256, 0, st>>>(h->ltab, h->params, h->wt); ++nl;
+  // loss + dL/d(outputs)
+  LossArgs la; memset(&la, 0, sizeof(la));
+  la.B = B; la.hw = OUT; la.J = J; la.S = S;
+  la.tiny = X.ptr(X.whole(h->buf_tiny)); la.poses = poses; la.cfgs = cfgs; la.coms = coms;
+  for (int s = 0; s < S; ++s) {
+    la.hm[s] = X.ptr(h->v_hm[s]); la.hm3[s] = X.ptr(h->v_hm3[s]); la.um[s] = X.ptr(h->v_um[s]); la.cs[s] = X.cs(h->v_hm[s]);
+    la.ghm[s] = X.gptr(h->v_hm[s]); la.ghm3[s] = X.gptr(h->v_hm3[s]); la.gum[s] = X.gptr(h->v_um[s]); la.gcs[s] = X.cs(h->v_hm[s]);
+  }
+  la.loss_acc = h->loss_acc;
+  nl += launch_loss(la, st);
+  nl += launch_wd(h->n_params, h->params, h->wdmask, h->grads, h->loss_acc + 3, st);
+  if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
+
+  for (int oi = (int)h->ops.size() - 1; oi >= 0; --oi) {
+    const Op& o = h->ops[oi];
+    switch (o.kind) {
+      case OP_CONV: {
+        const Layer& L = h->layers[o.layer];
+        const float* dy = X.gptr(o.out); const int dy_cs = X.cs(o.out);
+        const size_t np = X.npix(o.out);
+        if (o.res.buf >= 0) {
+          nl += apply_fills(h, X, o.gw_res, st);
+          nl += launch_copy_view(np, o.res.C, dy, dy_cs, X.gptr(o.res), X.cs(o.res), o.gw_res.acc, nullptr, st);
+        }
+        float* dz = h->scratch; const int dz_cs = (L.cout + 3) / 4 * 4;
+        if (L.brn) {
+          View rv = X.whole(o.raw);
+          double* sums = h->sums_bw + L.sum_off;
+          nl += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
+          nl += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
+                                     h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
+        } else {
+          nl += launch_bias_bwd(np, L.cout, dy, dy_cs, X.ptr(o.out), X.cs(o.out), L.relu, o.dropout_tag >= 0, dz, dz_cs, h->grads + L.p_off, st);
+        }
+        WgradProblem wp; memset(&wp, 0, sizeof(wp));
+        wp.x = X.ptr(o.in); wp.x_cs = X.cs(o.in); wp.dy = dz; wp.dy_cs = dz_cs;
+        wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin; wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout;
+        wp.k = L.k; wp.stride = L.stride; wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
+        wp.dw = h->grads + L.w_off;
+        nl += launch_wgrad_simt(wp, st);
+        if (o.need_dgrad) {
+          nl += apply_fills(h, X, o.gw_in, st);
+          ConvProblem p; memset(&p, 0, sizeof(p));
+          p.x = dz; p.x_cs = dz_cs; p.B = B; p.H = L.out_hw; p.W = L.out_hw; p.Cin = L.cout;
+          p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin; p.k = L.k; p.stride = 1;
+          p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
+          p.w = h->wt + L.w_off;
+          p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
+          nl += run_conv(h, p, h->precision, st);
+        }
+        break;
+      }
+      case OP_POOL: {
+        const Buf& bi = h->bufs[o.in.buf];
+        nl += apply_fills(h, X, o.gw_in, st);
+        nl += launch_maxpool_bwd(B, bi.H, bi.W, o.in.C, o.k, X.ptr(o.in), X.cs(o.in), X.gptr(o.out), X.cs(o.out),
+                                 X.gptr(o.in), X.cs(o.in), o.gw_in.acc, st);
+        break;
+      }
+      case OP_UPADD: {
+        const Buf& bo = h->bufs[o.out.buf];
+        nl += apply_fills(h, X, o.gw_in, st);
+        nl += launch_copy_view(X.npix(o.out), o.out.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.in), X.cs(o.in), o.gw_in.acc, nullptr, st);
+        nl += apply_fills(h, X, o.gw_res, st);
+        nl += launch_upadd_bwd_lo(B, bo.H, bo.W, o.out.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.res), X.cs(o.res), o.gw_res.acc, st);
+        break;
+      }
+      case OP_MASKCOPY:
+        nl += apply_fills(h, X, o.gw_in, st);
+        nl += launch_copy_view(X.npix(o.in), o.in.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.in), X.cs(o.in), o.gw_in.acc,
+                               X.ptr(X.whole(h->buf_tiny)), st);
+        break;
+    }
+  }
+  h->launches += nl;
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+// device-side tables are created lazily (first dr_bind) so that dr_create / dr_get_layer work on a
+// machine without a GPU (CPU-only CI checks the layer table against the oracle).
+int init_device(dr_handle* h) {
+  if (h->ltab) return DR_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  std::vector<LayerDev> tab(h->layers.size());
+  std::vector<float> wdm(h->n_params, 0.f);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    const Layer& L = h->layers[i];
+    tab[i] = LayerDev{L.cout, L.brn, L.k * L.k, L.cin, L.w_off, L.p_off, L.s_off, L.aff_off};
+    if (L.wd > 0) for (int64_t j = 0; j < (int64_t)L.k * L.k * L.cin * L.cout; ++j) wdm[L.w_off + j] = L.wd;
+  }
+  CUDA_TRY(h, cudaMalloc(&h->ltab, tab.size() * sizeof(LayerDev)));
+  CUDA_TRY(h, cudaMalloc(&h->wdmask, wdm.size() * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->aff, h->n_aff * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->bstat, h->n_bstat * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->sums, h->n_sums * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->sums_bw, h->n_sums * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->loss_acc, 4 * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->clamp_dev, sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemcpy(h->ltab, tab.data(), tab.size() * sizeof(LayerDev), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->wdmask, wdm.data(), wdm.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->ws_bytes += tab.size() * sizeof(LayerDev) + (wdm.size() + h->n_aff + h->n_bstat) * sizeof(float) + 2 * h->n_sums * sizeof(double);
+  return DR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int dr_version(void) { return DR_VERSION; }
+
+int dr_create(dr_handle** out, const dr_config* cfg) {
+  if (!out || !cfg) return DR_ERR_ARG;
+  *out = nullptr;
+  if (cfg->kernel_size != 3 || cfg->in_hw != 128 || cfg->out_hw != 32 || cfg->num_stack < 1 || cfg->num_stack > 4 ||
+      cfg->num_fea < 8 || cfg->num_fea % 4 != 0 || cfg->num_jnt < 1 || cfg->num_jnt > 64 || cfg->max_batch < 1)
+    return DR_ERR_ARG;
+  dr_handle* h = new dr_handle();
+  h->cfg = *cfg;
+  h->precision = cfg->precision;
+  Builder b{h, 0, 0, 0};
+  b.build();
+  *out = h;
+  return DR_OK;
+}
+
+int dr_destroy(dr_handle* h) {
+  if (!h) return DR_ERR_ARG;
+  cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
+  cudaFree(h->wt); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
+  cudaFree(h->clamp_dev); cudaFree(h->ltab);
+  delete h;
+  return DR_OK;
+}
+
+const char* dr_last_error(const dr_handle* h) { return h ? h->err.c_str() : "null handle"; }
+size_t dr_param_count(const dr_handle* h) { return h ? h->n_params : 0; }
+size_t dr_state_count(const dr_handle* h) { return h ? h->n_state : 0; }
+int dr_num_layers(const dr_handle* h) { return h ? (int)h->layers.size() : 0; }
+int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
+size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes : 0; }
+
+int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out) {
+  if (!h || !out || idx < 0 || idx >= (int)h->layers.size()) return DR_ERR_ARG;
+  const Layer& L = h->layers[idx];
+  memset(out, 0, sizeof(*out));
+  memcpy(out->name, L.name, sizeof(out->name));
+  out->k = L.k; out->stride = L.stride; out->cin = L.cin; out->cout = L.cout; out->brn = L.brn; out->relu = L.relu;
+  out->wd = L.wd; out->w_off = L.w_off; out->p_off = L.p_off; out->s_off = L.brn ? L.s_off : -1;
+  out->in_hw = L.in_hw; out->out_hw = L.out_hw;
+  return DR_OK;
+}
+
+int dr_bind(dr_handle* h, float* params, float* state, float* grads, float* adam_m, float* adam_v) {
+  if (!h || !params || !state) return DR_ERR_ARG;
+  h->params = params; h->state = state; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
+  return init_device(h);
+}
+
+int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream) {
+  if (!h) return DR_ERR_ARG;
+  if (!h->params || !h->state) return fail(h, DR_ERR_STATE, "dr_bind() not called");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches += launch_init_trunc_normal(h->n_params, h->params, stddev, seed, st);
+  init_state_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state); ++h->launches;
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_norm_dm(dr_handle* h, int B, int hw, const float* dm_mm, const float* coms, float* out, void* stream) {
+  if (!h || !dm_mm || !coms || !out || B < 1 || hw < 1) return DR_ERR_ARG;
+  h->launches += launch_norm_dm(B, hw, dm_mm, coms, out, (cudaStream_t)stream);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+static int copy_outputs(dr_handle* h, int B, float* const* hm, float* const* hm3, float* const* um, cudaStream_t st) {
+  Exec X{h, B, st};
+  for (int s = 0; s < h->cfg.num_stack; ++s) {
+    if (hm && hm[s]) h->launches += launch_gather_outputs(X.npix(h->v_hm[s]), h->v_hm[s].C, X.ptr(h->v_hm[s]), X.cs(h->v_hm[s]), hm[s], st);
+    if (hm3 && hm3[s]) h->launches += launch_gather_outputs(X.npix(h->v_hm3[s]), h->v_hm3[s].C, X.ptr(h->v_hm3[s]), X.cs(h->v_hm3[s]), hm3[s], st);
+    if (um && um[s]) h->launches += launch_gather_outputs(X.npix(h->v_um[s]), h->v_um[s].C, X.ptr(h->v_um[s]), X.cs(h->v_um[s]), um[s], st);
+  }
+  return DR_OK;
+}
+
+int dr_forward(dr_handle* h, int B, const float* dm_mm, const float* coms,
+               float* const* hm, float* const* hm3, float* const* um,
+               int is_training, int update_state, uint64_t dropout_seed, void* stream) {
+  if (!h || !dm_mm || !coms) return DR_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(h, B, dm_mm, coms, is_training, update_state, dropout_seed, st);
+  if (rc) return rc;
+  copy_outputs(h, B, hm, hm3, um, st);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_vote(dr_handle* h, int B, int H, int W, int J,
+            const float* hm, const float* hm3, const float* um, const float* dm_norm,
+            const float* cfgs, const float* coms,
+            float* xyz_mm, int32_t* top5_idx, int32_t* clamp_count, void* stream) {
+  if (!h || !hm || !hm3 || !um || !dm_norm || !cfgs || !coms || !xyz_mm) return DR_ERR_ARG;
+  if (B < 1 || H < 1 || W < 1 || J < 1 || J > 64 || H * W < 5) return DR_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (clamp_count) CUDA_TRY(h, cudaMemsetAsync(clamp_count, 0, sizeof(int32_t), st));
+  h->launches += launch_vote(B, H, W, J, hm, J, hm3, J, um, 3 * J, dm_norm, cfgs, coms, xyz_mm, top5_idx, clamp_count, st);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const float* coms,
+             float* xyz_mm, int32_t* top5_idx, void* stream) {
+  if (!h || !dm_mm || !cfgs || !coms || !xyz_mm) return DR_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(h, B, dm_mm, coms, 0, 0, 0, st);
+  if (rc) return rc;
+  Exec X{h, B, st};
+  const int s = h->cfg.num_stack - 1, J = h->cfg.num_jnt, OUT = h->cfg.out_hw;
+  h->launches += launch_vote(B, OUT, OUT, J, X.ptr(h->v_hm[s]), X.cs(h->v_hm[s]), X.ptr(h->v_hm3[s]), X.cs(h->v_hm3[s]),
+                             X.ptr(h->v_um[s]), X.cs(h->v_um[s]), X.ptr(X.whole(h->buf_tiny)), cfgs, coms, xyz_mm, top5_idx,
+                             h->clamp_dev, st);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses_mm,
+                     const float* cfgs, const float* coms, float* loss_out,
+                     uint64_t dropout_seed, int update_state, void* stream) {
+  if (!h || !dm_mm || !poses_mm || !cfgs || !coms) return DR_ERR_ARG;
+  if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(h, B, dm_mm, coms, 1, update_state, dropout_seed, st);
+  if (rc) return rc;
+  return backward_impl(h, B, poses_mm, cfgs, coms, loss_out, st);
+}
+
+int dr_zero_grads(dr_handle* h, void* stream) {
+  if (!h) return DR_ERR_ARG;
+  if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
+  CUDA_TRY(h, cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(float), (cudaStream_t)stream));
+  return DR_OK;
+}
+
+int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_t step, void* stream) {
+  if (!h || accum_steps < 1 || world < 1 || step < 1) return DR_ERR_ARG;
+  if (!h->grads || !h->adam_m || !h->adam_v || !h->params) return fail(h, DR_ERR_STATE, "grads / adam buffers not bound");
+  const double b1 = 0.5, b2 = 0.999;                       // hourglass_um_crop_tiny.py:77,439
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step)));
+  h->launches += launch_adam(h->n_params, h->params, h->grads, h->adam_m, h->adam_v, 1.0f / (float)(accum_steps * world), 0.2f,
+                             lr_t, (float)b1, (float)b2, 1e-8f, (cudaStream_t)stream);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {
+  if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;
+  if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
+  const Layer& L = h->layers[layer];
+  ConvProblem p; memset(&p, 0, sizeof(p));
+  p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
+  p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
+  p.w = h->params + L.w_off; p.y = y; p.y_cs = L.cout;
+  h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const float* dy, float* dx, float* dw, int precision, void* stream) {
+  if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !dy || B < 1) return DR_ERR_ARG;
+  if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layer& L = h->layers[layer];
+  const size_t nw = (size_t)L.k * L.k * L.cin * L.cout;
+  if (dw) {
+    CUDA_TRY(h, cudaMemsetAsync(dw, 0, nw * sizeof(float), st));
+    WgradProblem wp; memset(&wp, 0, sizeof(wp));
+    wp.x = x; wp.x_cs = L.cin; wp.dy = dy; wp.dy_cs = L.cout; wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin;
+    wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout; wp.k = L.k; wp.stride = L.stride;
+    wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride); wp.dw = dw;
+    h->launches += launch_wgrad_simt(wp, st);
+  }
+  if (dx) {
+    if (L.stride != 1) return fail(h, DR_ERR_UNSUPPORTED, "dgrad only for stride-1 convs (the stem conv has no input gradient)");
+    float* wt = nullptr;
+    CUDA_TRY(h, cudaMalloc(&wt, nw * sizeof(float)));
+    h->launches += launch_transpose_weights(L.k, L.cin, L.cout, h->params + L.w_off, wt, st);
+    ConvProblem p; memset(&p, 0, sizeof(p));
+    p.x = dy; p.x_cs = L.cout; p.B = B; p.H = L.out_hw; p.W = L.out_hw; p.Cin = L.cout; p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin;
+    p.k = L.k; p.stride = 1; p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, 1);
+    p.w = wt; p.y = dx; p.y_cs = L.cin;
+    h->launches += run_conv(h, p, precision, st);
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(wt);
+  }
+  CUDA_TRY(h, cudaPeekAtLastError());
+  return DR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,552 @@
+// ew.cu -- HBM-bound elementwise / reduction kernels around the convolutions.  All tensors are NHWC
+// fp32 "views": a pointer already offset to the first channel plus a channel stride, so producers
+// write straight into concat buffers (tf.concat on the path costs no copy).
+//
+// Reference ops replaced (under /root/reference):
+//   data/preprocess.py:176-187 norm_dm                              -> norm_dm_kernel
+//   network/um_v1.py:109-121 tiny_dm / uu / vv / uvd                -> make_uvd_kernel
+//   network/slim/ops.py:640-669 max_pool (+ TF MaxPoolGrad)         -> maxpool_kernel / maxpool_bwd_kernel
+//   network/slim/ops.py:671-677 upsampling_nearest + add um_v1.py:69 -> upadd_kernel / upadd_bwd_lo_kernel
+//   network/um_v1.py:146-148 tf.where depth mask                    -> copy_view_kernel(mask)
+//   network/slim/ops.py:130-171 Batch ReNorm (train)                -> channel_stats / brn_finalize / brn_apply
+//   network/slim/ops.py:173-180 BRN eval                            -> fold_affine
+//   model/hourglass_um_crop_tiny.py:195-274,323-371 GT synthesis + l2 losses -> loss_kernel
+//   network/slim/losses.py:56-72 l2_regularizer                     -> wd_kernel
+//   model/train_single_gpu.py:86-88 + tf.train.AdamOptimizer        -> adam_kernel
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int EW_T = 256;
+inline int blocks_for(size_t n, int per_block = EW_T, int cap = 148 * 16) {
+  size_t b = (n + per_block - 1) / per_block;
+  if (b > (size_t)cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void norm_dm_kernel(int B, int npix, const float* __restrict__ dm, const float* __restrict__ coms,
+                               float* __restrict__ out) {
+  size_t n = (size_t)B * npix;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / npix);
+    float cz = coms[b * 3 + 2];
+    float max_depth = cz + 300.0f * 0.5f, min_depth = cz - 300.0f * 0.5f;
+    float d = dm[i];
+    bool m = (d < max_depth) && (d > (min_depth - 300.0f * 0.5f));
+    out[i] = m ? __fdiv_rn(__fsub_rn(d, min_depth), 300.0f) : -1.0f;
+  }
+}
+
+__global__ void make_uvd_kernel(int B, int in_hw, int out_hw, const float* __restrict__ x0, float* __restrict__ tiny,
+                                UvdDst dst) {
+  size_t n = (size_t)B * out_hw * out_hw;
+  int s = in_hw / out_hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / (out_hw * out_hw));
+    int r = (int)(i - (size_t)b * out_hw * out_hw);
+    int y = r / out_hw, x = r - y * out_hw;
+    float d = x0[((size_t)b * in_hw + y * s) * in_hw + x * s];
+    float uu = (float)x / (float)(out_hw / 2) - 1.0f;
+    float vv = (float)y / (float)(out_hw / 2) - 1.0f;
+    if (tiny) tiny[i] = d;
+    for (int k = 0; k < dst.n; ++k) {
+      float* p = dst.p[k] + i * dst.cs[k];
+      p[0] = uu; p[1] = vv; p[2] = d;
+    }
+  }
+}
+
+// SAME max pool stride 2: k=2 (pad 0,0) or k=3 (pad 0 before, 1 after on even inputs); padding never wins
+__global__ void maxpool_kernel(int B, int H, int W, int C, int k, const float* __restrict__ x, int x_cs,
+                               float* __restrict__ y, int y_cs) {
+  int Ho = H / 2, Wo = W / 2;
+  size_t n = (size_t)B * Ho * Wo * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    int ox = (int)(pix % Wo); int oy = (int)((pix / Wo) % Ho); int b = (int)(pix / ((size_t)Wo * Ho));
+    float m = -INFINITY;
+    for (int dy = 0; dy < k; ++dy) {
+      int iy = oy * 2 + dy; if (iy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        int ix = ox * 2 + dx; if (ix >= W) continue;
+        float v = x[((size_t)(b * H + iy) * W + ix) * x_cs + c];
+        m = v > m ? v : m;
+      }
+    }
+    y[pix * y_cs + c] = m;
+  }
+}
+
+// gather form of MaxPoolGrad: input pixel (iy,ix) receives dy of every window whose FIRST maximum (row-major
+// scan, strict >) it is -- the convention of TF's and PyTorch's max-pool backward.
+__global__ void maxpool_bwd_kernel(int B, int H, int W, int C, int k, const float* __restrict__ x, int x_cs,
+                                   const float* __restrict__ dy, int dy_cs, float* __restrict__ dx, int dx_cs, int accumulate) {
+  int Ho = H / 2, Wo = W / 2;
+  size_t n = (size_t)B * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    int ix = (int)(pix % W); int iy = (int)((pix / W) % H); int b = (int)(pix / ((size_t)W * H));
+    float g = 0.f;
+    // windows (oy,ox) covering (iy,ix): oy*2 <= iy <= oy*2+k-1
+    int oy_lo = (iy - (k - 1) + 1) / 2; if (iy - (k - 1) < 0) oy_lo = 0;
+    int ox_lo = (ix - (k - 1) + 1) / 2; if (ix - (k - 1) < 0) ox_lo = 0;
+    for (int oy = oy_lo; oy <= iy / 2 && oy < Ho; ++oy) {
+      for (int ox = ox_lo; ox <= ix / 2 && ox < Wo; ++ox) {
+        float m = -INFINITY; int ay = -1, ax = -1;
+        for (int ddy = 0; ddy < k; ++ddy) {
+          int yy = oy * 2 + ddy; if (yy >= H) continue;
+          for (int ddx = 0; ddx < k; ++ddx) {
+            int xx = ox * 2 + ddx; if (xx >= W) continue;
+            float v = x[((size_t)(b * H + yy) * W + xx) * x_cs + c];
+            if (v > m) { m = v; ay = yy; ax = xx; }
+          }
+        }
+        if (ay == iy && ax == ix) g += dy[((size_t)(b * Ho + oy) * Wo + ox) * dy_cs + c];
+      }
+    }
+    float* o = dx + pix * dx_cs + c;
+    *o = accumulate ? *o + g : g;
+  }
+}
+
+__global__ void upadd_kernel(int B, int H, int W, int C, const float* __restrict__ a, int a_cs,
+                             const float* __restrict__ lo, int lo_cs, float* __restrict__ y, int y_cs) {
+  size_t n = (size_t)B * H * W * C;
+  int Hl = H / 2, Wl = W / 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    int x = (int)(pix % W); int yy = (int)((pix / W) % H); int b = (int)(pix / ((size_t)W * H));
+    float v = a[pix * a_cs + c] + lo[((size_t)(b * Hl + (yy >> 1)) * Wl + (x >> 1)) * lo_cs + c];
+    y[pix * y_cs + c] = v;
+  }
+}
+
+__global__ void upadd_bwd_lo_kernel(int B, int H, int W, int C, const float* __restrict__ dy, int dy_cs,
+                                    float* __restrict__ dlo, int dlo_cs, int accumulate) {
+  int Hl = H / 2, Wl = W / 2;
+  size_t n = (size_t)B * Hl * Wl * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    int x = (int)(pix % Wl); int y = (int)((pix / Wl) % Hl); int b = (int)(pix / ((size_t)Wl * Hl));
+    const float* r0 = dy + ((size_t)(b * H + 2 * y) * W + 2 * x) * dy_cs + c;
+    const float* r1 = r0 + (size_t)W * dy_cs;
+    float g = (r0[0] + r0[dy_cs]) + (r1[0] + r1[dy_cs]);
+    float* o = dlo + pix * dlo_cs + c;
+    *o = accumulate ? *o + g : g;
+  }
+}
+
+__global__ void copy_view_kernel(size_t npix, int C, const float* __restrict__ src, int src_cs, float* __restrict__ dst,
+                                 int dst_cs, int accumulate, const float* __restrict__ tiny_mask) {
+  size_t n = npix * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    float v = src[pix * src_cs + c];
+    if (tiny_mask && tiny_mask[pix] < -0.9f) v = 0.f;
+    float* o = dst + pix * dst_cs + c;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+__global__ void fill_view_kernel(size_t npix, int C, float* __restrict__ dst, int dst_cs, float v) {
+  size_t n = npix * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    dst[pix * dst_cs + c] = v;
+  }
+}
+
+// per-channel sum / sum of squares in double.  block (32 channels, 8 pixel lanes); grid (C/32, pixel blocks)
+__global__ void channel_stats_kernel(size_t npix, int C, const float* __restrict__ x, int x_cs, double* __restrict__ sums) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
+      float v = x[p * x_cs + c];
+      a += (double)v; b += (double)v * (double)v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(sums + c, a); atomicAdd(sums + C + c, b);
+  }
+}
+
+// state layout per BRN conv: mov_mean[C], mov_var[C], biased_mean[C], biased_var[C], r_max, d_max, curr_t, local_step
+__global__ void brn_finalize_kernel(int C, double n, const double* __restrict__ sums, const float* __restrict__ bg,
+                                    float* __restrict__ state, float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
+  const float eps = 0.001f, decay = 0.99f;
+  const float r_max = state[4 * C], d_max = state[4 * C + 1], t = state[4 * C + 2], step = state[4 * C + 3];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double mean_d = sums[c] / n;
+    double var_d = sums[C + c] / n - mean_d * mean_d;
+    if (var_d < 0) var_d = 0;
+    float mean = (float)mean_d, var = (float)var_d;
+    float mov_mean = state[c], mov_var = state[C + c];
+    float stdv = sqrtf(var + eps), mov_std = sqrtf(mov_var + eps);
+    float r = fminf(fmaxf(stdv / mov_std, 1.0f / r_max), r_max);               // ops.py:158-159
+    float d = fminf(fmaxf((mean - mov_mean) / mov_std, -d_max), d_max);       // ops.py:161-162
+    float inv_std = rsqrtf(var + eps);
+    inv_std = 1.0f / sqrtf(var + eps);
+    float beta = bg[c], gamma = bg[C + c];
+    // y = ((x-mean)*inv_std*r + d)*gamma + beta = x*a + b
+    float a = inv_std * r * gamma;
+    float b = (d - mean * inv_std * r) * gamma + beta;
+    aff[c] = a; aff[C + c] = b;
+    bstat[c] = mean; bstat[C + c] = inv_std; bstat[2 * C + c] = r; bstat[3 * C + c] = d;
+    if (update_state) {                                                       // ops.py:134-137, zero-debiased EMA
+      float bm = state[2 * C + c], bv = state[3 * C + c];
+      bm -= (bm - mean) * (1.0f - decay);
+      bv -= (bv - var) * (1.0f - decay);
+      float corr = 1.0f - powf(decay, step + 1.0f);
+      state[2 * C + c] = bm; state[3 * C + c] = bv;
+      state[c] = bm / corr; state[C + c] = bv / corr;
+    }
+  }
+  __syncthreads();
+  if (update_state && threadIdx.x == 0) {
+    state[4 * C] = 3.0f / (1.0f + 2.0f * expf(-t));                          // ops.py:141-144
+    state[4 * C + 1] = 5.0f / (5000.0f * expf(-2.0f * t));                   // ops.py:146-149
+    state[4 * C + 2] = t + 1e-5f;                                             // ops.py:151-153
+    state[4 * C + 3] = step + 1.0f;
+  }
+}
+
+__global__ void fold_affine_kernel(int C, int brn, const float* __restrict__ pb, const float* __restrict__ state, float* __restrict__ aff) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (brn) {                                                                   // ops.py:173-180
+    float inv = (1.0f / sqrtf(state[C + c] + 0.001f)) * pb[C + c];
+    aff[c] = inv; aff[C + c] = pb[c] - state[c] * inv;
+  } else {
+    aff[c] = 1.0f; aff[C + c] = pb[c];
+  }
+}
+
+__global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ raw, int raw_cs, const float* __restrict__ aff,
+                                 int relu, const float* __restrict__ res, int res_cs, float* __restrict__ y, int y_cs) {
+  size_t n = npix * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    float v = raw[pix * raw_cs + c] * aff[c] + aff[C + c];
+    if (relu) v = fmaxf(v, 0.f);
+    if (res) v += res[pix * res_cs + c];
+    y[pix * y_cs + c] = v;
+  }
+}
+
+__global__ void brn_bwd_reduce_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ raw,
+                                      int raw_cs, const float* __restrict__ aff, const float* __restrict__ bstat, int relu,
+                                      double* __restrict__ sums) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    float sa = aff[c], sb = aff[C + c], mean = bstat[c], inv_std = bstat[C + c];
+    for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
+      float x = raw[p * raw_cs + c];
+      float g = dy[p * dy_cs + c];
+      if (relu && !(x * sa + sb > 0.f)) g = 0.f;
+      float xh = (x - mean) * inv_std;
+      a += (double)g; b += (double)g * (double)xh;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(sums + c, a); atomicAdd(sums + C + c, b);
+  }
+}
+
+__global__ void brn_bwd_apply_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ raw,
+                                     int raw_cs, const float* __restrict__ aff, const float* __restrict__ bstat,
+                                     const float* __restrict__ bg, int relu, const double* __restrict__ sums,
+                                     float* __restrict__ draw, int draw_cs, float* __restrict__ gparam) {
+  size_t n = npix * C;
+  const double inv_n = 1.0 / (double)npix;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    float sa = aff[c], sb = aff[C + c], mean = bstat[c], inv_std = bstat[C + c], r = bstat[2 * C + c];
+    float gamma = bg[C + c];
+    float x = raw[pix * raw_cs + c];
+    float g = dy[pix * dy_cs + c];
+    if (relu && !(x * sa + sb > 0.f)) g = 0.f;
+    float xh = (x - mean) * inv_std;
+    float mg = (float)(sums[c] * inv_n), mgx = (float)(sums[C + c] * inv_n);
+    draw[pix * draw_cs + c] = gamma * r * inv_std * (g - mg - xh * mgx);
+  }
+  // dbeta = sum g ; dgamma = sum g*(xhat*r + d) = r*sum_gx + d*sum_g      (block 0 only)
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float r = bstat[2 * C + c], d = bstat[3 * C + c];
+      gparam[c] += (float)sums[c];
+      gparam[C + c] += (float)((double)r * sums[C + c] + (double)d * sums[c]);
+    }
+  }
+}
+
+__global__ void bias_bwd_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ out, int out_cs,
+                                int relu, int dropout, float* __restrict__ dz, int dz_cs, float* __restrict__ gbias) {
+  __shared__ float s1[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (c < C) {
+    for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
+      float g = dy[p * dy_cs + c];
+      if (relu) g = out[p * out_cs + c] > 0.f ? (dropout ? g * 2.0f : g) : 0.f;
+      dz[p * dz_cs + c] = g;
+      a += g;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) a += s1[i][threadIdx.x];
+    atomicAdd(gbias + c, a);
+  }
+}
+
+// GT synthesis + 3 l2 losses + dL/d(out) for every stack; one thread per (b, pixel), loop over joints.
+__global__ void loss_kernel(LossArgs a) {
+  const int hw = a.hw, J = a.J;
+  const size_t n = (size_t)a.B * hw * hw;
+  double l_hm = 0.0, l_hm3 = 0.0, l_um = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / (hw * hw)); int r = (int)(i - (size_t)b * hw * hw);
+    int py = r / hw, px = r - py * hw;
+    const float* cfg = a.cfgs + b * 6; const float* com = a.coms + b * 3;
+    float w_ratio = cfg[4] / (float)hw, h_ratio = cfg[5] / (float)hw;
+    float fx = cfg[0] / w_ratio, fy = cfg[1] / h_ratio, cx = cfg[2] / w_ratio, cy = cfg[3] / h_ratio;
+    float d = a.tiny[i];
+    float z = d < -0.99f ? com[2] + 150.0f : d * 300.0f + (com[2] - 150.0f);
+    float X = ((float)px - cx) * (z / fx), Y = ((float)py - cy) * (z / fy);
+    float Pn0 = (X - com[0]) / 100.0f, Pn1 = (Y - com[1]) / 100.0f, Pn2 = (z - com[2]) / 100.0f;
+    for (int j = 0; j < J; ++j) {
+      const float* pose = a.poses + (size_t)b * 3 * J + 3 * j;
+      float o0 = (pose[0] - com[0]) / 100.0f - Pn0;
+      float o1 = (pose[1] - com[1]) / 100.0f - Pn1;
+      float o2 = (pose[2] - com[2]) / 100.0f - Pn2;
+      float dist = sqrtf(o0 * o0 + o1 * o1 + o2 * o2);
+      float g3 = fmaxf((0.8f - dist) / 0.8f, 0.f);                              // _hm_3d :206-208
+      float dd = 0.8f - g3 * 0.8f;                                               // _um :260
+      bool m = dd < (0.8f - 1e-2f);
+      float u0 = m ? o0 / dd : 0.f, u1 = m ? o1 / dd : 0.f, u2 = m ? o2 / dd : 0.f;
+      float uu = pose[0] * fx / pose[2] + cx, vv = pose[1] * fy / pose[2] + cy;  // util.py:20
+      float e0 = (float)px - uu, e1 = (float)py - vv;
+      float g2 = fmaxf(4.0f - sqrtf(e0 * e0 + e1 * e1), 0.f) / 4.0f;             // _hm_2d :243-244
+      for (int s = 0; s < a.S; ++s) {
+        size_t o = i * a.cs[s], go = i * a.gcs[s];
+        float dh = a.hm[s][o + j] - g2;
+        float dh3 = a.hm3[s][o + j] - g3;
+        float q0 = a.um[s][o + 3 * j] - u0, q1 = a.um[s][o + 3 * j + 1] - u1, q2 = a.um[s][o + 3 * j + 2] - u2;
+        a.ghm[s][go + j] = dh; a.ghm3[s][go + j] = dh3;
+        a.gum[s][go + 3 * j] = q0; a.gum[s][go + 3 * j + 1] = q1; a.gum[s][go + 3 * j + 2] = q2;
+        l_hm += 0.5 * (double)dh * dh; l_hm3 += 0.5 * (double)dh3 * dh3;
+        l_um += 0.5 * ((double)q0 * q0 + (double)q1 * q1 + (double)q2 * q2);
+      }
+    }
+  }
+  __shared__ double red[3][EW_T / 32];
+  for (int off = 16; off > 0; off >>= 1) {
+    l_hm += __shfl_xor_sync(0xffffffffu, l_hm, off);
+    l_hm3 += __shfl_xor_sync(0xffffffffu, l_hm3, off);
+    l_um += __shfl_xor_sync(0xffffffffu, l_um, off);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = l_hm; red[1][w] = l_hm3; red[2][w] = l_um; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int k = 0; k < EW_T / 32; ++k) s += red[threadIdx.x][k];
+    atomicAdd(a.loss_acc + threadIdx.x, s);
+  }
+}
+
+__global__ void wd_kernel(size_t n, const float* __restrict__ p, const float* __restrict__ wdm, float* __restrict__ g, double* __restrict__ reg) {
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float w = wdm[i];
+    if (w != 0.f) { float v = p[i]; g[i] += w * v; acc += 0.5 * (double)w * v * v; }
+  }
+  __shared__ double red[EW_T / 32];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int k = 0; k < EW_T / 32; ++k) s += red[k]; atomicAdd(reg, s); }
+}
+
+__global__ void finish_loss_kernel(const double* __restrict__ acc, float* __restrict__ out5) {
+  double t = acc[0] + acc[1] + acc[2] + acc[3];
+  out5[0] = (float)t; out5[1] = (float)acc[0]; out5[2] = (float)acc[1]; out5[3] = (float)acc[2]; out5[4] = (float)acc[3];
+}
+
+__global__ void adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            float inv_scale, float clip, float lr_t, float b1, float b2, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * inv_scale;
+    gi = fminf(fmaxf(gi, -clip), clip);
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// wt[(kk-1-tap)][n][c] = w[tap][c][n] : 180-degree rotated, in/out swapped (dgrad == forward conv with wt)
+__global__ void transpose_weights_kernel(int kk, int cin, int cout, const float* __restrict__ w, float* __restrict__ wt) {
+  size_t n = (size_t)kk * cin * cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cin); size_t r = i / cin; int o = (int)(r % cout); int tap = (int)(r / cout);
+    wt[i] = w[((size_t)(kk - 1 - tap) * cin + c) * cout + o];
+  }
+}
+
+__global__ void init_trunc_normal_kernel(size_t n, float* __restrict__ p, float stddev, uint64_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // Box-Muller on a splitmix64 stream, re-drawn outside +-2 sigma (tf.truncated_normal_initializer, ops.py:272)
+    uint64_t ctr = i * 16;
+    float z = 0.f;
+    for (int t = 0; t < 16; ++t) {
+      uint64_t x = (ctr + t) + seed * 0x9E3779B97F4A7C15ull;
+      x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+      float u1 = ((uint32_t)(x >> 40) + 1.0f) * (1.0f / 16777217.0f);
+      float u2 = (uint32_t)((x >> 8) & 0xFFFFFF) * (1.0f / 16777216.0f);
+      z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+      if (fabsf(z) <= 2.0f) break;
+      z = 0.f;
+    }
+    p[i] = z * stddev;
+  }
+}
+
+__global__ void gather_outputs_kernel(size_t npix, int C, const float* __restrict__ src, int src_cs, float* __restrict__ dst) {
+  size_t n = npix * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); size_t pix = i / C;
+    dst[i] = src[pix * src_cs + c];
+  }
+}
+
+}  // namespace
+
+int launch_norm_dm(int B, int hw, const float* dm, const float* coms, float* out, cudaStream_t st) {
+  size_t n = (size_t)B * hw * hw;
+  norm_dm_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, hw * hw, dm, coms, out);
+  return 1;
+}
+int launch_make_uvd(int B, int in_hw, int out_hw, const float* x0, float* tiny, UvdDst dst, cudaStream_t st) {
+  size_t n = (size_t)B * out_hw * out_hw;
+  make_uvd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, in_hw, out_hw, x0, tiny, dst);
+  return 1;
+}
+int launch_maxpool(int B, int H, int W, int C, int k, const float* x, int x_cs, float* y, int y_cs, cudaStream_t st) {
+  size_t n = (size_t)B * (H / 2) * (W / 2) * C;
+  maxpool_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, k, x, x_cs, y, y_cs);
+  return 1;
+}
+int launch_maxpool_bwd(int B, int H, int W, int C, int k, const float* x, int x_cs, const float* dy, int dy_cs,
+                       float* dx, int dx_cs, int accumulate, cudaStream_t st) {
+  size_t n = (size_t)B * H * W * C;
+  maxpool_bwd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, k, x, x_cs, dy, dy_cs, dx, dx_cs, accumulate);
+  return 1;
+}
+int launch_upadd(int B, int H, int W, int C, const float* a, int a_cs, const float* lo, int lo_cs, float* y, int y_cs, cudaStream_t st) {
+  size_t n = (size_t)B * H * W * C;
+  upadd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, a, a_cs, lo, lo_cs, y, y_cs);
+  return 1;
+}
+int launch_upadd_bwd_lo(int B, int H, int W, int C, const float* dy, int dy_cs, float* dlo, int dlo_cs, int accumulate, cudaStream_t st) {
+  size_t n = (size_t)B * (H / 2) * (W / 2) * C;
+  upadd_bwd_lo_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, dy, dy_cs, dlo, dlo_cs, accumulate);
+  return 1;
+}
+int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* dst, int dst_cs, int accumulate,
+                     const float* tiny_mask, cudaStream_t st) {
+  copy_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, src, src_cs, dst, dst_cs, accumulate, tiny_mask);
+  return 1;
+}
+int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st) {
+  fill_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dst, dst_cs, v);
+  return 1;
+}
+static dim3 stats_grid(size_t npix, int C) {
+  int gx = (C + 31) / 32;
+  size_t gy = (npix + 8 * 32 - 1) / (8 * 32);          // >= 32 pixels per thread before splitting further
+  size_t cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  return dim3(gx, (unsigned)gy);
+}
+int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums, cudaStream_t st) {
+  channel_stats_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums);
+  return 1;
+}
+int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
+                        float* aff, float* bstat, int update_state, cudaStream_t st) {
+  brn_finalize_kernel<<<1, 256, 0, st>>>(C, n, sums, beta_gamma, state, aff, bstat, update_state);
+  return 1;
+}
+int launch_fold_affine(int C, int brn, const float* pb, const float* state, float* aff, cudaStream_t st) {
+  fold_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, brn, pb, state, aff);
+  return 1;
+}
+int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
+                     const float* res, int res_cs, float* y, int y_cs, cudaStream_t st) {
+  brn_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
+  return 1;
+}
+int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
+                          const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st) {
+  brn_bwd_reduce_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, relu, sums);
+  return 1;
+}
+int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
+                         const float* aff, const float* bstat, const float* beta_gamma, int relu,
+                         const double* sums, float* draw, int draw_cs, float* gparam, cudaStream_t st) {
+  brn_bwd_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, beta_gamma, relu,
+                                                              sums, draw, draw_cs, gparam);
+  return 1;
+}
+int launch_bias_bwd(size_t npix, int C, const float* dy, int dy_cs, const float* out, int out_cs, int relu, int dropout,
+                    float* dz, int dz_cs, float* gbias, cudaStream_t st) {
+  bias_bwd_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, dy, dy_cs, out, out_cs, relu, dropout, dz, dz_cs, gbias);
+  return 1;
+}
+int launch_loss(const LossArgs& a, cudaStream_t st) {
+  size_t n = (size_t)a.B * a.hw * a.hw;
+  loss_kernel<<<blocks_for(n, EW_T, 148 * 8), EW_T, 0, st>>>(a);
+  return 1;
+}
+int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, double* reg_acc, cudaStream_t st) {
+  wd_kernel<<<blocks_for(n, EW_T * 4, 148 * 4), EW_T, 0, st>>>(n, params, wdmask, grads, reg_acc);
+  return 1;
+}
+int launch_finish_loss(const double* acc, float* out5, cudaStream_t st) {
+  finish_loss_kernel<<<1, 1, 0, st>>>(acc, out5);
+  return 1;
+}
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
+                float lr_t, float b1, float b2, float eps, cudaStream_t st) {
+  adam_kernel<<<blocks_for(n, EW_T * 4, 148 * 8), EW_T, 0, st>>>(n, p, g, m, v, inv_scale, clip, lr_t, b1, b2, eps);
+  return 1;
+}
+int launch_transpose_weights(int k, int cin, int cout, const float* w, float* wt, cudaStream_t st) {
+  size_t n = (size_t)k * k * cin * cout;
+  transpose_weights_kernel<<<blocks_for(n), EW_T, 0, st>>>(k * k, cin, cout, w, wt);
+  return 1;
+}
+int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st) {
+  init_trunc_normal_kernel<<<blocks_for(n), EW_T, 0, st>>>(n, p, stddev, seed);
+  return 1;
+}
+int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, float* dst, cudaStream_t st) {
+  gather_outputs_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, src, src_cs, dst);
+  return 1;
+}

@@ -1,0 +1,167 @@
+"""DenseRegEngine: thin Python owner of the flat parameter/state/gradient tensors and the dr_handle.
+
+Mirrors the reference's plugin seams:
+  network.um_v1.detect_net(dm_inputs, cfgs, coms, num_jnt, is_training)   -> DenseRegEngine.forward
+  JointDetectionModel._xyz_estimation(hms, oms, hm3s, dms, cfgs, coms)    -> DenseRegEngine.vote
+  JointDetectionModel.test / loss / opt                                   -> infer / loss_backward / optimizer_step
+All tensors are torch CUDA tensors used as raw buffers; every call goes through the C-ABI.
+"""
+import ctypes as C
+import torch
+from . import _ffi
+
+
+class DenseRegError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.int32), (t.dtype, t.is_cuda)
+    return C.c_void_p(t.data_ptr())
+
+
+class DenseRegEngine:
+    def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="fp32", device=0,
+                 kernel_size=3, training=True):
+        if not torch.cuda.is_available():
+            raise DenseRegError("densereg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _ffi.load()
+        self.device = torch.device("cuda", device)
+        self.S, self.F, self.J = num_stack, num_fea, num_jnt
+        self.max_batch = max_batch
+        cfg = _ffi.DrConfig(num_stack=num_stack, num_fea=num_fea, kernel_size=kernel_size, num_jnt=num_jnt,
+                            in_hw=128, out_hw=32, max_batch=max_batch,
+                            precision=_ffi.PRECISIONS[precision] if isinstance(precision, str) else precision,
+                            device=device)
+        self._h = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        rc = self.lib.dr_create(C.byref(self._h), C.byref(cfg))
+        if rc != 0:
+            raise DenseRegError("dr_create failed with %d" % rc)
+        self.n_params = self.lib.dr_param_count(self._h)
+        self.n_state = self.lib.dr_state_count(self._h)
+        kw = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(self.n_params, **kw)
+        self.state = torch.zeros(self.n_state, **kw)
+        self.grads = torch.zeros(self.n_params, **kw) if training else None
+        self.adam_m = torch.zeros(self.n_params, **kw) if training else None
+        self.adam_v = torch.zeros(self.n_params, **kw) if training else None
+        self._check(self.lib.dr_bind(self._h, _ptr(self.params), _ptr(self.state), _ptr(self.grads),
+                                     _ptr(self.adam_m), _ptr(self.adam_v)))
+        self.loss_buf = torch.zeros(5, **kw)
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise DenseRegError("libdensereg_sm100 error %d: %s" % (rc, self.lib.dr_last_error(self._h).decode()))
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def layers(self):
+        out = []
+        for i in range(self.lib.dr_num_layers(self._h)):
+            li = _ffi.DrLayerInfo()
+            self._check(self.lib.dr_get_layer(self._h, i, C.byref(li)))
+            out.append(dict(name=li.name.decode(), k=li.k, stride=li.stride, cin=li.cin, cout=li.cout, brn=li.brn,
+                            relu=li.relu, wd=li.wd, w_off=li.w_off, p_off=li.p_off, s_off=li.s_off,
+                            in_hw=li.in_hw, out_hw=li.out_hw))
+        return out
+
+    def init_params(self, seed=0, stddev=0.01):
+        self._check(self.lib.dr_init_params(self._h, seed, stddev, self._stream()))
+
+    def load_flat(self, params, state=None):
+        """Copy flat fp32 parameter (and BRN state) vectors (e.g. from a checkpoint) into the bound buffers."""
+        self.params.copy_(params.to(self.device, torch.float32))
+        if state is not None:
+            self.state.copy_(state.to(self.device, torch.float32))
+
+    # ------------------------------------------------------------------------------------------
+    def norm_dm(self, dm_mm, coms):
+        B, hw = dm_mm.shape[0], dm_mm.shape[1]
+        out = torch.empty_like(dm_mm)
+        self._check(self.lib.dr_norm_dm(self._h, B, hw, _ptr(dm_mm), _ptr(coms), _ptr(out), self._stream()))
+        return out
+
+    def forward(self, dm_mm, coms, is_training=False, update_state=False, dropout_seed=0):
+        """detect_net on raw depth crops (B,128,128,1) mm.  Returns dict of per-stack NHWC tensors like the
+        reference's end_points {'hm_outs','hm3_outs','um_outs'} (network/um_v1.py:72-75,170-172)."""
+        B = dm_mm.shape[0]
+        kw = dict(dtype=torch.float32, device=self.device)
+        hms = [torch.empty(B, 32, 32, self.J, **kw) for _ in range(self.S)]
+        hm3s = [torch.empty(B, 32, 32, self.J, **kw) for _ in range(self.S)]
+        ums = [torch.empty(B, 32, 32, 3 * self.J, **kw) for _ in range(self.S)]
+        arr = lambda ts: (C.c_void_p * self.S)(*[t.data_ptr() for t in ts])
+        self._check(self.lib.dr_forward(self._h, B, _ptr(dm_mm), _ptr(coms), arr(hms), arr(hm3s), arr(ums),
+                                        int(is_training), int(update_state), dropout_seed, self._stream()))
+        return {"hm_outs": hms, "hm3_outs": hm3s, "um_outs": ums}
+
+    def vote(self, hm, hm3, um, dm_norm, cfgs, coms, return_top5=False):
+        """_resume_om + _xyz_estimation + unnorm_xyz_pose on dense maps -> xyz mm (B,3J)."""
+        B, H, W, J = hm.shape
+        xyz = torch.empty(B, 3 * J, dtype=torch.float32, device=self.device)
+        top5 = torch.empty(B, J, 5, dtype=torch.int32, device=self.device)
+        clamp = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.dr_vote(self._h, B, H, W, J, _ptr(hm), _ptr(hm3), _ptr(um), _ptr(dm_norm), _ptr(cfgs),
+                                     _ptr(coms), _ptr(xyz), _ptr(top5), _ptr(clamp), self._stream()))
+        return (xyz, top5, clamp) if return_top5 else xyz
+
+    def infer(self, dm_mm, cfgs, coms, out=None, top5=None):
+        """JointDetectionModel.test: raw crops -> xyz mm (B,3J)."""
+        B = dm_mm.shape[0]
+        if out is None:
+            out = torch.empty(B, 3 * self.J, dtype=torch.float32, device=self.device)
+        self._check(self.lib.dr_infer(self._h, B, _ptr(dm_mm), _ptr(cfgs), _ptr(coms), _ptr(out), _ptr(top5), self._stream()))
+        return out
+
+    def zero_grads(self):
+        self._check(self.lib.dr_zero_grads(self._h, self._stream()))
+
+    def loss_backward(self, dm_mm, poses_mm, cfgs, coms, dropout_seed=0, update_state=True):
+        """One micro-batch of JointDetectionModel.loss + backward; grads accumulate.  Returns the device
+        tensor {total, hm, hm3, um, reg} (no sync)."""
+        B = dm_mm.shape[0]
+        self._check(self.lib.dr_loss_backward(self._h, B, _ptr(dm_mm), _ptr(poses_mm), _ptr(cfgs), _ptr(coms),
+                                              _ptr(self.loss_buf), dropout_seed, int(update_state), self._stream()))
+        return self.loss_buf
+
+    def optimizer_step(self, step, lr, accum_steps=1, world=1):
+        self._check(self.lib.dr_optimizer_step(self._h, accum_steps, world, float(lr), int(step), self._stream()))
+
+    def debug_conv(self, layer, x, precision="fp32"):
+        L = self.layers()[layer]
+        B = x.shape[0]
+        y = torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
+        self._check(self.lib.dr_debug_conv(self._h, layer, B, _ptr(x), _ptr(y), _ffi.PRECISIONS[precision], self._stream()))
+        return y
+
+    def debug_conv_bwd(self, layer, x, dy, precision="fp32", want_dx=True):
+        L = self.layers()[layer]
+        dx = torch.empty_like(x) if want_dx else None
+        dw = torch.empty(L["k"] * L["k"] * L["cin"] * L["cout"], dtype=torch.float32, device=self.device)
+        self._check(self.lib.dr_debug_conv_bwd(self._h, layer, x.shape[0], _ptr(x), _ptr(dy), _ptr(dx), _ptr(dw),
+                                               _ffi.PRECISIONS[precision], self._stream()))
+        return dx, dw
+
+    @property
+    def launch_count(self):
+        return int(self.lib.dr_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.dr_workspace_bytes(self._h))

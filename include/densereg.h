@@ -1,0 +1,158 @@
+/* densereg.h -- C-ABI of libdensereg_sm100.so, the B200-native replacement for the
+ * denseReg hot path (depth crop -> um_v1 stacked hourglass -> {hm,hm3,um} -> offset vote
+ * -> joint xyz in mm; plus the data-parallel training step).
+ *
+ * The reference (melonwan/denseReg) has no FFI: its seams are Python call signatures.  Each
+ * entry point below names the reference interface (file:line under /root/reference) that a
+ * binding would replace.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer owned by the caller (PyTorch tensors'
+ *     data_ptr()); layout NHWC fp32 exactly like the reference's TF tensors; the library owns
+ *     only its handle, an activation workspace and scratch.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns without synchronising unless stated.
+ *   - return 0 on success, a negative dr_status otherwise; dr_last_error() gives the message.
+ *     Nothing throws across the boundary.  One handle per device per process; not re-entrant.
+ */
+#ifndef DENSEREG_H_
+#define DENSEREG_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_VERSION 100
+#define DR_API __attribute__((visibility("default")))
+
+typedef enum {
+  DR_OK = 0,
+  DR_ERR_ARG = -1,      /* bad argument / shape                 */
+  DR_ERR_CUDA = -2,     /* CUDA runtime error                   */
+  DR_ERR_STATE = -3,    /* call order (e.g. buffers not bound)  */
+  DR_ERR_NOMEM = -4,
+  DR_ERR_UNSUPPORTED = -5
+} dr_status;
+
+/* conv arithmetic */
+typedef enum {
+  DR_PREC_FP32 = 0,     /* SIMT FFMA, fp32 accumulate (parity path)                        */
+  DR_PREC_TF32 = 1,     /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM                 */
+  DR_PREC_TF32X3 = 2    /* tcgen05 3-pass split TF32 (fp32-class accuracy)                 */
+} dr_precision;
+
+/* Mirrors the reference flag surface that shapes the graph:
+ * model/hourglass_um_crop_tiny.py:29-62 (--num_stack --num_fea --kernel_size), dataset jnt_num
+ * (data/icvl.py:17, nyu.py:40-45, msra.py:17), input/output size (:82-87). */
+typedef struct {
+  int32_t num_stack;     /* FLAGS.num_stack, default 2   */
+  int32_t num_fea;       /* FLAGS.num_fea, default 128   */
+  int32_t kernel_size;   /* FLAGS.kernel_size, must be 3 */
+  int32_t num_jnt;       /* 16 icvl / 14 nyu / 21 msra   */
+  int32_t in_hw;         /* 128                          */
+  int32_t out_hw;        /* 32                           */
+  int32_t max_batch;     /* workspace is sized for this  */
+  int32_t precision;     /* dr_precision                 */
+  int32_t device;        /* CUDA ordinal                 */
+  int32_t reserved[7];
+} dr_config;
+
+typedef struct dr_handle dr_handle;
+
+/* one row of the conv table, in TF variable-creation order of network/um_v1.py:71-185 */
+typedef struct {
+  char name[48];
+  int32_t k, stride, cin, cout, brn, relu;
+  float wd;              /* l2 weight decay (network/slim/losses.py:56-72), 0 for inter-stack convs */
+  int64_t w_off;         /* offset of HWIO weights in the flat parameter buffer                    */
+  int64_t p_off;         /* beta[cout],gamma[cout] (brn) or biases[cout]                           */
+  int64_t s_off;         /* BRN state: mov_mean, mov_var, biased_mean, biased_var [cout each],
+                            r_max, d_max, curr_t, local_step                                       */
+  int32_t in_hw, out_hw;
+} dr_layer_info;
+
+DR_API int dr_version(void);
+
+/* Graph construction == network/um_v1.py:detect_net (:71-185) + JointDetectionModel.__init__
+ * (model/hourglass_um_crop_tiny.py:92-127). */
+DR_API int dr_create(dr_handle** out, const dr_config* cfg);
+DR_API int dr_destroy(dr_handle* h);
+DR_API const char* dr_last_error(const dr_handle* h);
+
+DR_API size_t dr_param_count(const dr_handle* h);   /* trainable fp32 scalars (tf.trainable_variables)       */
+DR_API size_t dr_state_count(const dr_handle* h);   /* non-trainable BRN state (network/slim/ops.py:100-128) */
+DR_API int dr_num_layers(const dr_handle* h);
+DR_API int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out);
+
+/* Caller-owned flat fp32 device buffers (replaces tf.Variable storage / tf.train.Saver contents,
+ * model/train_single_gpu.py:108).  grads/adam_m/adam_v may be NULL for inference-only use. */
+DR_API int dr_bind(dr_handle* h, float* params, float* state, float* grads, float* adam_m, float* adam_v);
+
+/* ops.py:272 truncated_normal(stddev), ops.py:86-128 BRN initial values.  Needs dr_bind first. */
+DR_API int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream);
+
+/* data/preprocess.py:176-187 norm_dm.  dm_mm (B,HW,HW), coms (B,3) -> out (B,HW,HW). */
+DR_API int dr_norm_dm(dr_handle* h, int B, int hw, const float* dm_mm, const float* coms, float* out, void* stream);
+
+/* JointDetectionModel.inference -> detect_net (hourglass_um_crop_tiny.py:186-191, um_v1.py:71-185),
+ * including norm_dm.  dm_mm (B,128,128,1) raw depth in mm, coms (B,3).
+ * hm/hm3/um: arrays of num_stack device pointers (B,32,32,J)/(B,32,32,J)/(B,32,32,3J); an entry or
+ * the array itself may be NULL to skip the copy-out.  is_training selects BRN batch statistics +
+ * dropout (ops.py:130-171, :726); update_state applies the BRN UPDATE_OPS (ops.py:134-153). */
+DR_API int dr_forward(dr_handle* h, int B, const float* dm_mm, const float* coms,
+               float* const* hm, float* const* hm3, float* const* um,
+               int is_training, int update_state, uint64_t dropout_seed, void* stream);
+
+/* JointDetectionModel._resume_om + _xyz_estimation + unnorm_xyz_pose
+ * (hourglass_um_crop_tiny.py:276-299, :743-785; data/preprocess.py:157-170,189-232).
+ * hm,hm3 (B,H,W,J), um (B,H,W,3J) dense; dm_norm (B,H,W) normalised depth at H x W; cfgs (B,6);
+ * coms (B,3).  xyz_mm (B,3J).  top5_idx (B,J,5) int32 and clamp_count (1 int32, re-projections
+ * that fell outside the map and were clamped) are optional. */
+DR_API int dr_vote(dr_handle* h, int B, int H, int W, int J,
+            const float* hm, const float* hm3, const float* um, const float* dm_norm,
+            const float* cfgs, const float* coms,
+            float* xyz_mm, int32_t* top5_idx, int32_t* clamp_count, void* stream);
+
+/* JointDetectionModel.test (hourglass_um_crop_tiny.py:442-462): norm_dm -> inference(eval) ->
+ * vote -> xyz in mm.  dm_mm (B,128,128,1), cfgs (B,6), coms (B,3) -> xyz_mm (B,3J). */
+DR_API int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const float* coms,
+             float* xyz_mm, int32_t* top5_idx, void* stream);
+
+/* JointDetectionModel.loss (hourglass_um_crop_tiny.py:323-371, no data_aug) + TF autodiff +
+ * accum_op (model/train_single_gpu.py:69-84): one micro-batch forward+backward; gradients are
+ * ADDED into the bound grads buffer.  poses_mm (B,3J).  loss_out: 5 floats on the DEVICE
+ * {total, hm, hm3, um, reg}. */
+DR_API int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses_mm,
+                     const float* cfgs, const float* coms, float* loss_out,
+                     uint64_t dropout_seed, int update_state, void* stream);
+
+/* reset_op (train_single_gpu.py:83) */
+DR_API int dr_zero_grads(dr_handle* h, void* stream);
+
+/* ave_grad + clip + Adam apply (train_single_gpu.py:86-88, hourglass_um_crop_tiny.py:436-439):
+ * g = clip(grads / (accum_steps*world), +-0.2); Adam(beta1 .5, beta2 .999, eps 1e-8) with TF's
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  `grads` must already hold the sum over micro-batches and
+ * ranks (the host does ONE all-reduce(sum) on it, replacing model/train_multi_gpu.py:16-39).
+ * step is the 1-based optimiser step. */
+DR_API int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_t step, void* stream);
+
+/* per-conv debug entry used by the parity tests: runs ONE conv of the table on caller data.
+ * x (B,H,W,cin) dense -> y (B,Ho,Wo,cout) = conv(x, W[idx]) (no BRN/bias/activation). */
+DR_API int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream);
+/* dgrad / wgrad of the same conv: dy (B,Ho,Wo,cout) -> dx (B,H,W,cin) (overwritten),
+ * dw (k*k*cin*cout) (overwritten). Either output may be NULL. */
+DR_API int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const float* dy,
+                      float* dx, float* dw, int precision, void* stream);
+
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+DR_API int64_t dr_launch_count(const dr_handle* h);
+
+/* activation workspace bytes currently allocated */
+DR_API size_t dr_workspace_bytes(const dr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSEREG_H_ */

@@ -1,0 +1,62 @@
+"""GPU parity: single convolutions (dr_debug_conv / dr_debug_conv_bwd through the C-ABI) vs the oracle's
+F.conv2d with explicit TF SAME padding, forward, dgrad and wgrad.  fp32 bar: 2e-5 of the output scale."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from gpu_util import cu, dump, relerr
+
+pytestmark = pytest.mark.gpu
+
+LAYERS = ["stem/conv_1", "stem/conv_2/c2", "stem/conv_2/skip", "stem/conv_4/c3", "s0/hg/n4/upper1/c2", "s0/hg/n1/lower1/c2",
+          "s0/hg/n2/lower3/c1", "s0/hm_out", "s0/hm3_res/c1", "s0/hm3_res/c2", "s0/hm3_res/skip", "s0/um_res1/c2",
+          "s0/um_comb/c2", "s0/um_full1", "s0/um_out", "s0/inter_out"]
+
+
+@pytest.fixture(scope="module")
+def setup(built_lib):
+    from densereg_b200.engine import DenseRegEngine
+    from oracle import um_v1_torch as U
+    eng = DenseRegEngine(num_stack=2, num_fea=128, num_jnt=14, max_batch=2, training=False)
+    net = U.Net(2, 128, 14)
+    p = net.init_params(1, stddev=0.1)
+    eng.load_flat(p)
+    return eng, net, p
+
+
+def oracle_conv(net, p, c, x_nhwc):
+    from oracle.um_v1_torch import same_pad
+    n = c.k * c.k * c.cin * c.cout
+    w = p[c.w_off:c.w_off + n].view(c.k, c.k, c.cin, c.cout).permute(3, 2, 0, 1)
+    x = x_nhwc.permute(0, 3, 1, 2)
+    pt, pb = same_pad(x.shape[2], c.k, c.stride); pl, pr = same_pad(x.shape[3], c.k, c.stride)
+    return F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, None, stride=c.stride).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_conv_forward_and_backward(setup, precision):
+    eng, net, p = setup
+    names = [l["name"] for l in eng.layers()]
+    rep = {}
+    for name in LAYERS:
+        c = net.by_name[name]; li = names.index(name)
+        hw = eng.layers()[li]["in_hw"]
+        g = torch.Generator().manual_seed(li)
+        x = torch.randn(2, hw, hw, c.cin, generator=g)
+        xr = x.clone().requires_grad_(True)
+        pr = p.clone().requires_grad_(True)
+        y_ref = oracle_conv(net, pr, c, xr)
+        dy = torch.randn(y_ref.shape, generator=g)
+        y_ref.backward(dy)
+        y = eng.debug_conv(li, cu(x), precision)
+        e = dict(fwd=relerr(y.cpu().numpy(), y_ref.detach().numpy()))
+        dx, dw = eng.debug_conv_bwd(li, cu(x), cu(dy), precision, want_dx=(c.stride == 1))
+        n = c.k * c.k * c.cin * c.cout
+        e["wgrad"] = relerr(dw.cpu().numpy(), pr.grad[c.w_off:c.w_off + n].numpy())
+        if c.stride == 1:
+            e["dgrad"] = relerr(dx.cpu().numpy(), xr.grad.numpy())
+        rep[name] = e
+    dump("conv_err_%s.json" % precision, rep)
+    tol = 2e-5 if precision == "fp32" else 2e-3
+    bad = {k: v for k, v in rep.items() if max(v.values()) > tol}
+    assert not bad, bad

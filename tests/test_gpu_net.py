@@ -1,0 +1,144 @@
+"""GPU parity: whole network forward (eval + train BRN), end-to-end inference (forward + vote), loss, gradients,
+BRN state updates and the Adam step, all through the C-ABI, vs the CPU oracle."""
+import os
+import numpy as np
+import pytest
+import torch
+from gpu_util import cu, dump, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make(S, F, J, B, seed, stddev, training=True):
+    from densereg_b200.engine import DenseRegEngine
+    from densereg_b200 import synth
+    from oracle import um_v1_torch as U
+    eng = DenseRegEngine(num_stack=S, num_fea=F, num_jnt=J, max_batch=B, training=training)
+    net = U.Net(S, F, J)
+    p, s = net.init_params(seed, stddev=stddev), net.init_state()
+    eng.load_flat(p, s)
+    data = synth.make_batch(B, J, seed=seed + 100)
+    return eng, net, p, s, data
+
+
+@pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 2), (2, 128, 16, 2), (2, 128, 21, 1)])
+def test_forward_eval_matches_oracle(built_lib, S, F, J, B):
+    from oracle import vote_numpy as V
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 3, 0.05, training=False)
+    x0 = torch.from_numpy(V.norm_dm(dms[..., 0], coms)[..., None])
+    hms, hm3s, ums = net.forward(p, s, x0, training=False)
+    out = eng.forward(cu(dms), cu(coms))
+    rep = {}
+    for st in range(S):
+        rep["hm%d" % st] = relerr(out["hm_outs"][st].cpu().numpy(), hms[st].numpy())
+        rep["hm3%d" % st] = relerr(out["hm3_outs"][st].cpu().numpy(), hm3s[st].numpy())
+        rep["um%d" % st] = relerr(out["um_outs"][st].cpu().numpy(), ums[st].numpy())
+    dump("net_eval_err_S%dF%dJ%d.json" % (S, F, J), rep)
+    assert max(rep.values()) < 1e-4, rep
+
+
+def test_norm_dm_bit_exact(built_lib):
+    from oracle import vote_numpy as V
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(1, 64, 16, 2, 5, 0.05, training=False)
+    out = eng.norm_dm(cu(dms), cu(coms)).cpu().numpy()
+    assert np.array_equal(out[..., 0], V.norm_dm(dms[..., 0], coms))
+
+
+def test_net_golden_statistics_on_gpu(built_lib):
+    from densereg_b200.engine import DenseRegEngine
+    from densereg_b200 import synth
+    from oracle import um_v1_torch as U
+    g = np.load(os.path.join(GOLD, "net_S1F64J16.npz"))
+    net = U.Net(1, 64, 16)
+    eng = DenseRegEngine(1, 64, 16, max_batch=1, training=False)
+    eng.load_flat(net.init_params(int(g["seed"]), stddev=float(g["stddev"])), net.init_state())
+    dms, poses, cfgs, coms = synth.make_batch(1, 16, seed=int(g["data_seed"]))
+    out = eng.forward(cu(dms), cu(coms))
+    assert relerr(out["hm_outs"][0].cpu().numpy()[0, ::4, ::4], g["hm_sub"]) < 1e-4
+    assert relerr(out["um_outs"][0].cpu().numpy()[0, ::4, ::4], g["um_sub"]) < 1e-4
+
+
+@pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 3), (2, 128, 14, 2)])
+def test_infer_end_to_end(built_lib, S, F, J, B):
+    """crops -> xyz mm through dr_infer vs oracle forward + oracle vote.  The vote given IDENTICAL maps is
+    index-exact (test_gpu_vote); end to end the maps differ by fp32 summation order, so top-5 lists are
+    compared where the oracle's 5th/6th score margin exceeds the map error, and xyz at 1e-3 mm on those joints."""
+    from oracle import vote_numpy as V
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 7, 0.05, training=False)
+    x0n = V.norm_dm(dms[..., 0], coms)
+    hms, hm3s, ums = net.forward(p, s, torch.from_numpy(x0n[..., None]), training=False)
+    d32 = V.tiny_dm(x0n)
+    ref_xyz, ref_top5, aux = V.xyz_estimation(hms[-1].numpy(), hm3s[-1].numpy(), ums[-1].numpy(), d32, cfgs, coms, return_aux=True)
+    top5 = torch.empty(B, J, 5, dtype=torch.int32, device="cuda")
+    xyz = eng.infer(cu(dms), cu(cfgs), cu(coms), top5=top5).cpu().numpy()
+    top5 = top5.cpu().numpy()
+    R = aux["refined"].reshape(B, -1, J)
+    srt = -np.sort(-R, axis=1)
+    margin = np.min(np.abs(np.diff(srt[:, :6, :], axis=1)), axis=1)           # (B,J) smallest gap among top-6
+    safe = margin > 1e-4 * np.abs(R).max()
+    same = (top5 == ref_top5).all(-1)
+    err = np.abs(xyz - ref_xyz).reshape(B, J, 3).max(-1)
+    dump("infer_e2e_S%dF%dJ%d.json" % (S, F, J), dict(frac_same_top5=float(same.mean()), frac_safe=float(safe.mean()),
+                                                     max_err_mm_same=float(np.nanmax(np.where(same, err, 0))),
+                                                     mean_joint_err_mm=float(np.nanmean(np.linalg.norm((xyz - ref_xyz).reshape(B, J, 3), axis=-1)))))
+    assert same[safe].all()
+    fin = np.isfinite(err) & same
+    assert (err[fin] <= 1e-3 * max(1.0, float(np.abs(ref_xyz[np.isfinite(ref_xyz)]).max()) / 100.0)).all()
+
+
+@pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 2), (2, 128, 16, 2)])
+def test_training_step_matches_oracle(built_lib, S, F, J, B):
+    from oracle import um_v1_torch as U
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 11, 0.05, training=True)
+    s_ref = s.clone()
+    L, g_ref, outs = U.loss_and_grads(net, p, s_ref, dms[..., 0], poses, cfgs, coms, dropout_seed=5)
+    # training-mode forward outputs
+    out = eng.forward(cu(dms), cu(coms), is_training=True, update_state=False, dropout_seed=5)
+    rep = {"fwd_um_last": relerr(out["um_outs"][-1].cpu().numpy(), outs[2][-1].detach().numpy()),
+           "fwd_hm_last": relerr(out["hm_outs"][-1].cpu().numpy(), outs[0][-1].detach().numpy())}
+    eng.zero_grads()
+    loss = eng.loss_backward(cu(dms), cu(poses), cu(cfgs), cu(coms), dropout_seed=5, update_state=True).cpu().numpy()
+    ref_loss = np.array([L["total"], L["hm"], L["hm3"], L["um"], L["reg"]])
+    rep["loss"] = float(np.abs(loss - ref_loss).max() / np.abs(ref_loss).max())
+    g = eng.grads.cpu().numpy(); gr = g_ref.numpy()
+    per = {}
+    for c in net.specs:
+        n = c.k * c.k * c.cin * c.cout
+        per[c.name] = float(np.linalg.norm(g[c.w_off:c.w_off + n] - gr[c.w_off:c.w_off + n]) /
+                            (np.linalg.norm(gr[c.w_off:c.w_off + n]) + 1e-20))
+        nb = 2 * c.cout if c.brn else c.cout
+        per[c.name + ":bg"] = float(np.linalg.norm(g[c.p_off:c.p_off + nb] - gr[c.p_off:c.p_off + nb]) /
+                                    (np.linalg.norm(gr[c.p_off:c.p_off + nb]) + 1e-20))
+    rep["grad_worst"] = max(per.values()); rep["grad_worst_name"] = max(per, key=per.get)
+    rep["grad_total"] = float(np.linalg.norm(g - gr) / np.linalg.norm(gr))
+    rep["state"] = relerr(eng.state.cpu().numpy(), s_ref.numpy())
+    # Adam step (train_single_gpu.py:86-88)
+    m = torch.zeros_like(p); v = torch.zeros_like(p); p_ref = p.clone()
+    U.adam_step(p_ref, g_ref.clone(), m, v, step=1, lr=1e-3, accum_steps=1, world=1)
+    eng.optimizer_step(step=1, lr=1e-3, accum_steps=1, world=1)
+    rep["adam_max_abs"] = float(np.abs(eng.params.cpu().numpy() - p_ref.numpy()).max())
+    dump("train_err_S%dF%dJ%d.json" % (S, F, J), dict(rep, per_layer=per))
+    assert rep["fwd_um_last"] < 2e-4 and rep["fwd_hm_last"] < 2e-4, rep
+    assert rep["loss"] < 1e-4, rep
+    assert rep["grad_total"] < 1e-3 and rep["grad_worst"] < 2e-2, rep
+    assert rep["state"] < 1e-4, rep
+    # clip makes the first Adam step +-lr for almost all weights; differences only where g is ~0
+    assert rep["adam_max_abs"] <= 2.1e-3, rep
+
+
+def test_grad_accumulation_equals_rank_sum(built_lib):
+    """allreduce-sum over N ranks == accumulation over N micro-batches (single GPU)."""
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(1, 64, 16, 4, 13, 0.05, training=True)
+    d, po, cf, co = cu(dms), cu(poses), cu(cfgs), cu(coms)
+    eng.zero_grads()
+    eng.loss_backward(d[:2].contiguous(), po[:2].contiguous(), cf[:2].contiguous(), co[:2].contiguous(), 1, update_state=False)
+    g0 = eng.grads.clone()
+    eng.zero_grads()
+    eng.loss_backward(d[2:].contiguous(), po[2:].contiguous(), cf[2:].contiguous(), co[2:].contiguous(), 2, update_state=False)
+    g1 = eng.grads.clone()
+    eng.zero_grads()
+    eng.loss_backward(d[:2].contiguous(), po[:2].contiguous(), cf[:2].contiguous(), co[:2].contiguous(), 1, update_state=False)
+    eng.loss_backward(d[2:].contiguous(), po[2:].contiguous(), cf[2:].contiguous(), co[2:].contiguous(), 2, update_state=False)
+    tot = eng.grads
+    assert float((tot - (g0 + g1)).norm() / tot.norm()) < 1e-5
