@@ -53,7 +53,7 @@ conv_fwd_kernel(ConvProblem p) {
   // ---- B-load mapping: float4 along n when Cout%4==0 (checked at run time per element group) ----
   const int b_n = (tid & 15) * 4;       // 16 threads x 4 = 64 columns
   const int b_k = tid >> 4;             // 16 rows
-  const bool b_vec = (p.Cout % 4 == 0);
+  const bool b_vec = (p.Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
 
   float acc[8][4];
 #pragma unroll

@@ -101,7 +101,7 @@ struct Builder {
   dr_handle* h;
   int F, J, S;
   int new_buf(int hw, int C, int raw = 0) {
-    Buf b; b.H = hw; b.W = hw; b.C = C; b.Cs = (C + 3) / 4 * 4; b.raw = raw;
+    Buf b; b.H = hw; b.W = hw; b.C = C; b.Cs = C == 1 ? 1 : (C + 3) / 4 * 4; b.raw = raw;   // 1-channel maps stay dense
     size_t& total = raw ? h->raw_per_crop : h->act_per_crop;
     b.off = total; total += (size_t)hw * hw * b.Cs;
     h->bufs.push_back(b);
@@ -590,6 +590,20 @@ const char* dr_last_error(const dr_handle* h) { return h ? h->err.c_str() : "nul
 size_t dr_param_count(const dr_handle* h) { return h ? h->n_params : 0; }
 size_t dr_state_count(const dr_handle* h) { return h ? h->n_state : 0; }
 int dr_num_layers(const dr_handle* h) { return h ? (int)h->layers.size() : 0; }
+int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, void* stream) {
+  if (!h || !dst || layer < 0 || layer >= (int)h->layers.size() || B < 1 || B > h->cap_B) return DR_ERR_ARG;
+  if (grad && !h->gact) return fail(h, DR_ERR_STATE, "no gradient workspace");
+  Exec X{h, B, (cudaStream_t)stream};
+  for (const Op& o : h->ops) {
+    if (o.kind == OP_CONV && o.layer == layer) {
+      h->launches += launch_gather_outputs(X.npix(o.out), o.out.C, grad ? X.gptr(o.out) : X.ptr(o.out), X.cs(o.out), dst, X.st);
+      CUDA_TRY(h, cudaPeekAtLastError());
+      return DR_OK;
+    }
+  }
+  return DR_ERR_ARG;
+}
+
 int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
 size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes : 0; }
 

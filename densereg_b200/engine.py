@@ -158,6 +158,12 @@ class DenseRegEngine:
                                                _ffi.PRECISIONS[precision], self._stream()))
         return dx, dw
 
+    def debug_get_output(self, layer, B, grad=False):
+        L = self.layers()[layer]
+        out = torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
+        self._check(self.lib.dr_debug_get_output(self._h, layer, B, _ptr(out), int(grad), self._stream()))
+        return out
+
     @property
     def launch_count(self):
         return int(self.lib.dr_launch_count(self._h))

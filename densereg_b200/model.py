@@ -1,0 +1,250 @@
+"""Host-side mirror of the reference's model object, drivers and flag surface for the hot path.
+
+  model/hourglass_um_crop_tiny.py:29-62   tf.app.flags             -> build_argparser (same names / defaults)
+  model/hourglass_um_crop_tiny.py:66-191  JointDetectionModel      -> JointDetectionModel (same attribute names)
+  model/train_single_gpu.py:37-177        train(model)             -> train(model): accumulate sub_batch micro-batches,
+                                                                      ONE all-reduce, clip +-0.2, Adam, staircase lr
+  model/train_multi_gpu.py:41-158         in-graph towers          -> one process per GPU + torch.distributed all_reduce
+  model/test_model.py:14-94               test(model)              -> test(model): writes name\\t%.4f... rows, '/'->'\\\\'
+  data/evaluation.py:9-18                 maxJntError/meanJntError -> evaluation helpers below
+
+All arithmetic happens in libdensereg_sm100.so through DenseRegEngine; this file only moves buffers,
+steps counters and writes text.  Datasets: none are on the box, so the dataset objects
+here generate seeded synthetic crops of each dataset's shape (densereg_b200/synth.py).
+"""
+import argparse
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import synth
+from .engine import DenseRegEngine
+
+
+def str2bool(v):
+    # the reference parses 'True'/'False' strings (readme.md:19,36)
+    return str(v).lower() in ("1", "true", "yes")
+
+
+def build_argparser():
+    p = argparse.ArgumentParser(description="densereg_b200 (flag surface of model/hourglass_um_crop_tiny.py:29-62)")
+    p.add_argument("--num_gpus", type=int, default=1)
+    p.add_argument("--batch_size", type=int, default=40)
+    p.add_argument("--debug_level", type=int, default=1)
+    p.add_argument("--sub_batch", type=int, default=5)
+    p.add_argument("--pid", type=int, default=0)
+    p.add_argument("--is_train", type=str2bool, default=True)
+    p.add_argument("--net_module", type=str, default="um_v1")
+    p.add_argument("--is_aug", type=str2bool, default=True)
+    p.add_argument("--dataset", type=str, default="nyu")
+    p.add_argument("--epoch", type=int, default=80)
+    p.add_argument("--num_stack", type=int, default=2)
+    p.add_argument("--num_fea", type=int, default=128)
+    p.add_argument("--kernel_size", type=int, default=3)
+    # additions (not in the reference): arithmetic mode and a bound on synthetic steps
+    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "tf32", "tf32x3"])
+    p.add_argument("--max_steps", type=int, default=0, help="stop after this many optimiser steps (0 = epoch schedule)")
+    p.add_argument("--test_num", type=int, default=0, help="number of synthetic test frames (0 = dataset's exact_num)")
+    return p
+
+
+class SyntheticDataset:
+    """Stands in for data/{icvl,nyu,msra}.py: same name / jnt_num / approximate_num / exact_num, synthetic crops."""
+    _SPEC = {  # name: (jnt_num, approximate_num, exact_num)   data/icvl.py:13-17,85  nyu.py:14,40-45,92  msra.py:14,17,70
+        "icvl": (16, 220 * 101, 1596),
+        "nyu": (14, 730 * 101, 8252),
+        "msra": (21, 85 * 801, 8499),
+    }
+
+    def __init__(self, name, subset, pid=0):
+        self.name, self.subset, self.pid = name, subset, pid
+        self.jnt_num, self.approximate_num, self.exact_num = self._SPEC[name]
+        self._cursor = 0
+
+    def batch(self, batch_size, seed):
+        """-> dms (B,128,128,1) mm, poses (B,3J) mm, cfgs (B,6), coms (B,3), names"""
+        dms, poses, cfgs, coms = synth.make_batch(batch_size, self.jnt_num, seed=seed)
+        names = ["%s_seq/image_%06d.png" % (self.subset, self._cursor + i) for i in range(batch_size)]
+        self._cursor += batch_size
+        return dms, poses, cfgs, coms, names
+
+
+def meanJntError(skel1, skel2):      # data/evaluation.py:15-18
+    d = np.asarray(skel1).reshape(-1, 3) - np.asarray(skel2).reshape(-1, 3)
+    return float(np.mean(np.sqrt(np.sum(d ** 2, axis=1))))
+
+
+def maxJntError(skel1, skel2):       # data/evaluation.py:9-12
+    d = np.asarray(skel1).reshape(-1, 3) - np.asarray(skel2).reshape(-1, 3)
+    return float(np.max(np.sqrt(np.sum(d ** 2, axis=1))))
+
+
+def format_result_row(name, xyz_val):
+    """model/test_model.py:74-75."""
+    res_str = "%s\t%s\n" % (name, "\t".join(format(float(pt), ".4f") for pt in xyz_val))
+    return res_str.replace("/", "\\")
+
+
+class JointDetectionModel:
+    """Same public attributes as the reference object (hourglass_um_crop_tiny.py:66-191, 436-543)."""
+    _init_lr = 0.001
+    _lr_decay_factor = 0.1
+    _adam_beta1 = 0.5
+    _num_epochs_per_decay = {"nyu": 10, "msra": 20, "icvl": 10}   # icvl undefined in the reference (:70-73) -> 10 (deviation)
+    _base_dir = "./exp/train_cache/"
+    TOWER_NAME = "um_v1"
+
+    def __init__(self, dataset, flags, val_dataset=None, device=0, world=1):
+        self._dataset, self._val_dataset, self.flags = dataset, val_dataset, flags
+        self._jnt_num = int(dataset.jnt_num)
+        self._num_batches_per_epoch = dataset.approximate_num / (flags.batch_size * flags.sub_batch)   # :109
+        self._max_steps = int(flags.epoch * self._num_batches_per_epoch)                                # :112
+        self._model_desc = "%s_%s_s%d_f%d" % (dataset.name, dataset.subset, flags.num_stack, flags.num_fea)
+        if flags.is_aug:
+            self._model_desc += "_daug"
+        self.world = world
+        self.engine = DenseRegEngine(flags.num_stack, flags.num_fea, self._jnt_num, max_batch=flags.batch_size,
+                                     precision=flags.precision, device=device, kernel_size=flags.kernel_size,
+                                     training=bool(flags.is_train))
+
+    # ---- trainer/tester contract -----------------------------------------------------
+    @property
+    def init_lr(self): return self._init_lr
+    @property
+    def lr_decay_factor(self): return self._lr_decay_factor
+    @property
+    def decay_steps(self): return int(self._num_batches_per_epoch * self._num_epochs_per_decay[self._dataset.name])
+    @property
+    def max_steps(self): return self._max_steps
+    @property
+    def name(self): return "%s_%s" % (self._model_desc, self.TOWER_NAME)
+    @property
+    def train_dir(self): return os.path.join(self._base_dir, self.name)
+    @property
+    def train_dataset(self): return self._dataset
+    @property
+    def val_dataset(self): return self._val_dataset
+    @property
+    def is_validate(self): return self._val_dataset is not None
+
+    def lr_at(self, step):
+        """tf.train.exponential_decay(staircase=True), train_single_gpu.py:45-49."""
+        return self._init_lr * self._lr_decay_factor ** (step // max(self.decay_steps, 1))
+
+    # ---- device-side calls --------------------------------------------------------------------------
+    def loss(self, dms, poses, cfgs, coms, dropout_seed=0):
+        """One micro-batch of model.loss + accum_op; device tensors in, device loss vector out."""
+        return self.engine.loss_backward(dms, poses, cfgs, coms, dropout_seed=dropout_seed)
+
+    def test(self, dms, cfgs, coms, out=None):
+        """model.test: raw crops -> xyz mm (B,3J)."""
+        return self.engine.infer(dms, cfgs, coms, out=out)
+
+    # ---- checkpoint: flat fp32 buffers in the reference's directory layout --------------
+    def save(self, step):
+        os.makedirs(self.train_dir, exist_ok=True)
+        path = os.path.join(self.train_dir, "model.ckpt-%d.pt" % step)
+        e = self.engine
+        torch.save(dict(step=step, params=e.params.cpu(), state=e.state.cpu(), adam_m=e.adam_m.cpu(), adam_v=e.adam_v.cpu(),
+                        config=dict(num_stack=e.S, num_fea=e.F, num_jnt=e.J)), path)
+        return path
+
+    def restore(self, step):
+        ck = torch.load(os.path.join(self.train_dir, "model.ckpt-%d.pt" % step), map_location="cpu")
+        e = self.engine
+        e.load_flat(ck["params"], ck["state"])
+        if e.adam_m is not None:
+            e.adam_m.copy_(ck["adam_m"]); e.adam_v.copy_(ck["adam_v"])
+        return ck["step"]
+
+
+def shard_batch(batch_size, rank, world):
+    """tf.split of the global minibatch across towers (train_multi_gpu.py:63-64) -> [lo, hi) of this rank."""
+    per = batch_size // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_gradients(grads, world):
+    """The ONE collective of the path: sum over ranks of the flat gradient buffer (replaces
+    train_multi_gpu.py:16-39 _average_gradients; the 1/world factor is folded into dr_optimizer_step)."""
+    if world > 1:
+        torch.distributed.all_reduce(grads, op=torch.distributed.ReduceOp.SUM)
+    return grads
+
+
+def train(model, rank=0, world=1, log=print):
+    """model/train_single_gpu.py:37-177 (loop :138-175) with per-rank sharding of each micro-batch."""
+    f = model.flags
+    eng = model.engine
+    max_steps = f.max_steps or model.max_steps
+    lo, hi = shard_batch(f.batch_size, rank, world)
+    dev = eng.device
+    t_log = time.time()
+    for step in range(max_steps):
+        eng.zero_grads()                                                           # reset_op :139
+        for sub in range(f.sub_batch):                                             # :140-148
+            dms, poses, cfgs, coms, _ = model.train_dataset.batch(f.batch_size, seed=step * f.sub_batch + sub)
+            tens = [torch.from_numpy(a[lo:hi]).pin_memory().to(dev, non_blocking=True) for a in (dms, poses, cfgs, coms)]
+            loss = model.loss(*tens, dropout_seed=(step * f.sub_batch + sub) * world + rank)
+        allreduce_gradients(eng.grads, world)
+        eng.optimizer_step(step + 1, model.lr_at(step), accum_steps=f.sub_batch, world=world)   # train_op :150
+        if step % 5 == 0 and rank == 0:                                            # :154-158
+            lv = loss.cpu().numpy()
+            assert not np.isnan(lv[0]), "Model diverged with loss = NaN"         # :147
+            dt = time.time() - t_log; t_log = time.time()
+            log("step %d, loss = %.2f (hm %.2f hm3 %.2f um %.2f reg %.3f) lr %.1e, %.3f sec/5 steps"
+                % (step, lv[0], lv[1], lv[2], lv[3], lv[4], model.lr_at(step), dt))
+        if (step + 1) % 100 == 0 and rank == 0:                                    # :168-175
+            model.save(step + 1)
+    return max_steps
+
+
+def test(model, out_path=None, log=print):
+    """model/test_model.py:14-94: loop batches, write result rows, return (mean, max) joint error vs the synthetic GT."""
+    f = model.flags
+    ds = model.val_dataset or model.train_dataset
+    total = f.test_num or ds.exact_num
+    out_path = out_path or os.path.join("exp", "result", "%s_b200.txt" % ds.name)
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    errs, maxs, n, step = [], [], 0, 0
+    dev = model.engine.device
+    with open(out_path, "w") as fo:
+        while n < total:
+            dms, poses, cfgs, coms, names = ds.batch(f.batch_size, seed=10_000 + step)
+            xyz = model.test(*[torch.from_numpy(a).to(dev) for a in (dms, cfgs, coms)]).cpu().numpy()
+            for xyz_val, gt_val, name in zip(xyz, poses, names):
+                errs.append(meanJntError(xyz_val, gt_val)); maxs.append(maxJntError(xyz_val, gt_val))
+                fo.write(format_result_row(name, xyz_val))
+                n += 1
+                if n >= total:
+                    break
+            step += 1
+    log("finish test: %d frames, mean joint err %.3f mm, mean max-joint err %.3f mm -> %s"
+        % (n, float(np.nanmean(errs)), float(np.nanmean(maxs)), out_path))
+    return float(np.nanmean(errs)), float(np.nanmean(maxs))
+
+
+def main(argv=None):
+    flags = build_argparser().parse_args(argv)
+    if flags.net_module != "um_v1":
+        raise SystemExit("only --net_module um_v1 exists (network/um_v1.py)")
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ds = SyntheticDataset(flags.dataset, "training" if flags.is_train else "testing", flags.pid)
+    val = SyntheticDataset(flags.dataset, "testing", flags.pid)
+    model = JointDetectionModel(ds, flags, val_dataset=val, device=local, world=world)
+    model.engine.init_params(seed=0)
+    if flags.is_train:
+        train(model, rank, world)
+    else:
+        test(model)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

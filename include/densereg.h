@@ -146,6 +146,11 @@ DR_API int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* 
 DR_API int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const float* dy,
                       float* dx, float* dw, int precision, void* stream);
 
+/* debug: copy the activation (grad=0) or its gradient (grad=1) that conv `layer` wrote in the last
+ * forward/backward into dst (B,Ho,Wo,cout) dense.  For the last conv of a residual block this is the block
+ * output (post-activation conv + skip), as in network/um_v1.py:48. */
+DR_API int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, void* stream);
+
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 DR_API int64_t dr_launch_count(const dr_handle* h);
 

@@ -263,7 +263,7 @@ class Net:
         """ops.dropout keep_prob 0.5 (ops.py:710-728): x * mask / 0.5; mask indexed in NHWC order."""
         B, C, H, W = x.shape
         m = dropout_mask(self.dropout_seed, tag, B * H * W * C).reshape(B, H, W, C)
-        m = torch.from_numpy(m).permute(0, 3, 1, 2)
+        m = torch.from_numpy(m).permute(0, 3, 1, 2).to(x.dtype)
         return x * m * 2.0
 
     def forward(self, params, state, x0_nhwc, training=False, dropout_seed=0):
@@ -283,8 +283,8 @@ class Net:
         hg_ins = self._residual(c3, "stem/conv_4", training)
         tiny = x[:, :, ::4, ::4]                                           # um_v1.py:111 (appendix B.3)
         oh, ow = tiny.shape[2], tiny.shape[3]
-        uu = (torch.arange(ow, dtype=torch.float32) / float(ow / 2) - 1.0).view(1, 1, 1, ow).expand(B, 1, oh, ow)
-        vv = (torch.arange(oh, dtype=torch.float32) / float(oh / 2) - 1.0).view(1, 1, oh, 1).expand(B, 1, oh, ow)
+        uu = (torch.arange(ow, dtype=torch.float32) / float(ow / 2) - 1.0).to(x.dtype).view(1, 1, 1, ow).expand(B, 1, oh, ow)
+        vv = (torch.arange(oh, dtype=torch.float32) / float(oh / 2) - 1.0).to(x.dtype).view(1, 1, oh, 1).expand(B, 1, oh, ow)
         uvd = torch.cat([uu, vv, tiny], dim=1)                             # um_v1.py:121
         hms, hm3s, ums = [], [], []
         for s in range(self.S):
@@ -362,12 +362,15 @@ def gt_maps(dm_mm, poses_mm, cfgs, coms, out_hw=32):
     return (t(x0[..., None].copy()), t(gt_hm), t(gt_hm3), t(gt_um.reshape(B, h, w, 3 * J)))
 
 
-def loss_and_grads(net, params, state, dm_mm, poses_mm, cfgs, coms, dropout_seed=0, update_state=True):
+def loss_and_grads(net, params, state, dm_mm, poses_mm, cfgs, coms, dropout_seed=0, update_state=True, dtype=torch.float32):
     """One micro-batch of hourglass_um_crop_tiny.py:323-371 (no data_aug) + autograd.
-    Returns dict(total, hm, hm3, um, reg), grad (flat, same layout as params), outputs."""
-    x0, gt_hm, gt_hm3, gt_um = gt_maps(dm_mm, poses_mm, cfgs, coms)
-    p = params.detach().clone().requires_grad_(True)
-    hms, hm3s, ums = net.forward(p, state, x0, training=True, dropout_seed=dropout_seed)
+    Returns dict(total, hm, hm3, um, reg), grad (flat, same layout as params), outputs.
+    dtype=torch.float64 runs the same graph in double (used by the tests to measure the fp32 noise floor of
+    the gradient: ReLU / BRN boundary flips make two fp32 implementations differ by ~3e-3 in the deep layers)."""
+    x0, gt_hm, gt_hm3, gt_um = [t.to(dtype) for t in gt_maps(dm_mm, poses_mm, cfgs, coms)]
+    p = params.detach().clone().to(dtype).requires_grad_(True)
+    st = state if dtype == torch.float32 else state.to(dtype)
+    hms, hm3s, ums = net.forward(p, st, x0, training=True, dropout_seed=dropout_seed)
     hm_l = sum(0.5 * ((e - gt_hm) ** 2).sum() for e in hms)               # tf.nn.l2_loss :353
     hm3_l = sum(0.5 * ((e - gt_hm3) ** 2).sum() for e in hm3s)            # :357
     um_l = sum(0.5 * ((e - gt_um) ** 2).sum() for e in ums)               # :363
@@ -376,7 +379,7 @@ def loss_and_grads(net, params, state, dm_mm, poses_mm, cfgs, coms, dropout_seed
     total.backward()
     if update_state:
         net.apply_state_updates()
-    return (dict(total=float(total), hm=float(hm_l), hm3=float(hm3_l), um=float(um_l), reg=float(reg)),
+    return (dict(total=total.item(), hm=hm_l.item(), hm3=hm3_l.item(), um=um_l.item(), reg=reg.item()),
             p.grad.detach(), (hms, hm3s, ums))
 
 

@@ -49,6 +49,7 @@ def test_conv_forward_and_backward(setup, precision):
         dy = torch.randn(y_ref.shape, generator=g)
         y_ref.backward(dy)
         y = eng.debug_conv(li, cu(x), precision)
+        torch.cuda.synchronize()
         e = dict(fwd=relerr(y.cpu().numpy(), y_ref.detach().numpy()))
         dx, dw = eng.debug_conv_bwd(li, cu(x), cu(dy), precision, want_dx=(c.stride == 1))
         n = c.k * c.k * c.cin * c.cout

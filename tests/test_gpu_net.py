@@ -38,6 +38,34 @@ def test_forward_eval_matches_oracle(built_lib, S, F, J, B):
     assert max(rep.values()) < 1e-4, rep
 
 
+def test_layerwise_trace_eval(built_lib):
+    """First-divergence map: every conv's output buffer vs the oracle trace (eval mode)."""
+    from oracle import vote_numpy as V
+    S, F, J, B = 1, 64, 16, 2
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 3, 0.05, training=False)
+    x0 = torch.from_numpy(V.norm_dm(dms[..., 0], coms)[..., None])
+    net.forward(p, s, x0, training=False)
+    eng.forward(cu(dms), cu(coms))
+    rep = {}
+    for i, c in enumerate(net.specs):
+        ref = net.trace[c.name]
+        if c.name.endswith("/c3"):          # block output = c3 + skip (um_v1.py:48)
+            blk = c.name[:-3]
+            first = net.by_name[blk + "/c1"]
+            continue_in = None
+            if (blk + "/skip") in net.by_name:
+                ref = ref + net.trace[blk + "/skip"]
+            else:
+                continue                     # identity skip: block input not traced; covered by the next conv
+        if c.name.endswith("/inter_out") or c.name.endswith("/inter_ll"):
+            continue
+        got = eng.debug_get_output(i, B).cpu().numpy()
+        rep[c.name] = relerr(got, ref.detach().permute(0, 2, 3, 1).numpy())
+    dump("layer_trace_eval.json", rep)
+    bad = {k: v for k, v in rep.items() if v > 1e-4}
+    assert not bad, list(bad.items())[:8]
+
+
 def test_norm_dm_bit_exact(built_lib):
     from oracle import vote_numpy as V
     eng, net, p, s, (dms, poses, cfgs, coms) = make(1, 64, 16, 2, 5, 0.05, training=False)
@@ -113,6 +141,25 @@ def test_training_step_matches_oracle(built_lib, S, F, J, B):
     rep["grad_worst"] = max(per.values()); rep["grad_worst_name"] = max(per, key=per.get)
     rep["grad_total"] = float(np.linalg.norm(g - gr) / np.linalg.norm(gr))
     rep["state"] = relerr(eng.state.cpu().numpy(), s_ref.numpy())
+    # fp32 noise floor of this gradient: the SAME oracle graph in float64.  ReLU / BRN sign flips at |z| ~ 1e-7 make
+    # any two fp32 evaluations differ by ~3e-3 in the deep layers; the bar for the GPU is "as close to the exact
+    # (float64) gradient as the fp32 reference restatement is" (factor 3, floor 3e-4), layer by layer.
+    _, g64, _ = U.loss_and_grads(net, p, s.clone(), dms[..., 0], poses, cfgs, coms, dropout_seed=5, update_state=False,
+                                 dtype=torch.float64)
+    g64 = g64.numpy()
+    noise_total = float(np.linalg.norm(gr - g64) / np.linalg.norm(g64))
+    gpu_total = float(np.linalg.norm(g - g64) / np.linalg.norm(g64))
+    rep["noise_total_fp32_vs_f64"] = noise_total; rep["gpu_total_vs_f64"] = gpu_total
+    worst_ratio, worst_layer = 0.0, None
+    for c in net.specs:
+        n = c.k * c.k * c.cin * c.cout
+        ref = g64[c.w_off:c.w_off + n]
+        noise = np.linalg.norm(gr[c.w_off:c.w_off + n] - ref) / np.linalg.norm(ref)
+        gpu = np.linalg.norm(g[c.w_off:c.w_off + n] - ref) / np.linalg.norm(ref)
+        ratio = gpu / max(noise, 3e-4)
+        if ratio > worst_ratio:
+            worst_ratio, worst_layer = float(ratio), c.name
+    rep["worst_gpu_over_noise"] = worst_ratio; rep["worst_gpu_over_noise_layer"] = worst_layer
     # Adam step (train_single_gpu.py:86-88)
     m = torch.zeros_like(p); v = torch.zeros_like(p); p_ref = p.clone()
     U.adam_step(p_ref, g_ref.clone(), m, v, step=1, lr=1e-3, accum_steps=1, world=1)
@@ -121,7 +168,9 @@ def test_training_step_matches_oracle(built_lib, S, F, J, B):
     dump("train_err_S%dF%dJ%d.json" % (S, F, J), dict(rep, per_layer=per))
     assert rep["fwd_um_last"] < 2e-4 and rep["fwd_hm_last"] < 2e-4, rep
     assert rep["loss"] < 1e-4, rep
-    assert rep["grad_total"] < 1e-3 and rep["grad_worst"] < 2e-2, rep
+    assert per["s%d/um_out" % (S - 1)] < 1e-5, rep          # no ReLU between the loss and this layer: exact to fp32
+    assert gpu_total <= 3 * noise_total + 3e-4, rep
+    assert worst_ratio <= 4.0, rep
     assert rep["state"] < 1e-4, rep
     # clip makes the first Adam step +-lr for almost all weights; differences only where g is ~0
     assert rep["adam_max_abs"] <= 2.1e-3, rep
