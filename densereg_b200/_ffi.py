@@ -49,6 +49,7 @@ SIGNATURES = {
     "dr_debug_conv_bwd": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, C.c_int, _P]),
     "dr_debug_get_output": (C.c_int, [_P, C.c_int, C.c_int, _F, C.c_int, _P]),
     "dr_launch_count": (C.c_int64, [_P]),
+    "dr_tc_launch_count": (C.c_int64, [_P]),
     "dr_workspace_bytes": (C.c_size_t, [_P]),
 }
 

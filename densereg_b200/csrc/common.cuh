@@ -24,6 +24,9 @@ struct ConvProblem {
   int Ho, Wo, Cout;
   int k, stride, pad_t, pad_l;
   const float* w;          // [k*k*Cin][Cout] row-major (TF HWIO flattened)
+  int flip_taps;           // read weight taps in reverse order (dgrad == conv with the 180-degree rotated filter)
+  const float* w_kmajor;   // tensor-core path: 16 B aligned K-major copy [tap][Cout][Cin] (hi part for 3xTF32), or null
+  const float* w_kmajor_lo;// 3xTF32: lo part
   float* y; int y_cs;      // output view
   // epilogue: v = acc*scale[n] + shift[n]; relu; dropout; + res; + beta*y_old
   const float* scale;      // may be null (=1)

@@ -86,7 +86,9 @@ conv_fwd_kernel(ConvProblem p) {
     // B
     int kb = k0 + b_k;
     if (kb < K) {
-      const float* wr = p.w + (size_t)kb * p.Cout + n0 + b_n;
+      int kbs = kb;
+      if (p.flip_taps) { int tp = kb / p.Cin; kbs = (p.k * p.k - 1 - tp) * p.Cin + (kb - tp * p.Cin); }
+      const float* wr = p.w + (size_t)kbs * p.Cout + n0 + b_n;
       if (b_vec && n0 + b_n + 3 < p.Cout) {
         float4 v = __ldg(reinterpret_cast<const float4*>(wr));
         b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;

@@ -1,4 +1,391 @@
-// conv_tc.cu -- tcgen05 / TMA implicit-GEMM convolution (placeholder until the kernel lands).
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma kind::tf32 -> TMEM (fp32 accumulate)
+//   -> tcgen05.ld -> fused epilogue (scale/shift | bias, ReLU, dropout, residual add, accumulate) -> NHWC view.
+//
+// Replaces tf.nn.conv2d (network/slim/ops.py:282) + the folded BRN/bias/ReLU/add epilogue of every stride-1
+// 1x1 / 3x3 conv of network/um_v1.py (97 % of the MACs), and -- with rotated/transposed weights -- TF's
+// Conv2DBackpropInput (dgrad).  Not a GEMM library call: the kernel below is the whole op.
+//
+// GEMM view per CTA: D[128 pixels, BN couts] = sum_{tap} sum_{c-block of 32} A_tap[128,32] * W_tap[32,BN].
+//   A tile: ONE 4-D TMA box (32 ch, W, 128/W rows [, images]) of the NHWC activation view at the tap's spatial
+//           offset; out-of-image coordinates are zero-filled by TMA, which IS the SAME padding.  Because a tile is
+//           whole image rows, smem row r == output pixel tile*128 + r.
+//   B tile: 3-D TMA box (32 ch, BN couts, 1 tap) of the K-major weight copy [tap][cout][cin]; channels past Cin
+//           and couts past Cout are zero-filled.
+//   Both K-major, SWIZZLE_128B (32 fp32 = 128 B rows, 8-row 1024 B atoms): UMMA smem descriptors advance
+//   32 B per K=8 MMA.  DR_PREC_TF32X3: a split warpgroup rewrites each landed A tile into hi (13 low mantissa bits
+//   cleared) + lo = a - hi, the weights are pre-split, and every k-step issues hi*lo + lo*hi + hi*hi into the
+//   same TMEM accumulator (fp32-class accuracy; algorithmic FLOPs unchanged).
+// Warp roles (192 / 320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
+//   (TMEM lane quarter = warp_idx % 4), warps 6-9 A splitter (3xTF32 only).  mbarrier full/empty ring.
 #include "common.cuh"
-bool conv_tc_eligible(const ConvProblem&) { return false; }
-int launch_conv_tc(const ConvProblem&, int, cudaStream_t) { return 0; }
+#include <cuda.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                       // fp32 elements per k-block = one 128 B swizzle row
+constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4; // 16 KB
+
+struct TcParams {
+  int M;                 // B*H*W output pixels
+  int H, W;              // spatial (stride 1: input == output size)
+  int Cin, Cout;
+  int ksz, pad;          // 1 or 3; pad (before)
+  int flip_taps;         // dgrad: weight tap index reversed (180-degree rotation)
+  int BN;                // N tile (multiple of 16, <= 256)
+  int kblocks_per_tap;   // ceil(Cin / 32)
+  int stages;
+  int tmem_cols;         // power of two >= BN, >= 32
+  float* y; int y_cs;
+  const float* scale; const float* shift; int relu;
+  const float* res; int res_cs; int accumulate;
+  int dropout; unsigned long long drop_seed; unsigned int drop_tag;
+};
+
+DR_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DR_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DR_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DR_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+DR_DEVINL void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+DR_DEVINL void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+DR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DR_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DR_DEVINL void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DR_DEVINL void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B | version 1 | layout 2
+DR_DEVINL uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+DR_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// dynamic smem layout (1024 B aligned): [stage][A hi 16K | (A lo 16K) | B hi BN*128 | (B lo BN*128)] ... barriers ... tmem ptr
+template <bool SPLIT3>
+__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.BN * TC_BK * 4;
+  const int stage_bytes = (SPLIT3 ? 2 : 1) * (A_TILE_BYTES + b_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* split_bar = empty_bar + p.stages;       // A tile split done (SPLIT3)
+  uint64_t* accum_bar = split_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
+  const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 128); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int pix0 = tile_m * TC_BM;
+      const int img = pix0 / (p.H * p.W);
+      const int y0 = (pix0 - img * p.H * p.W) / p.W;
+      const uint32_t tx = (uint32_t)(A_TILE_BYTES + (SPLIT3 ? 2 : 1) * b_bytes);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = kb / p.kblocks_per_tap;
+        const int c0 = (kb - tap * p.kblocks_per_tap) * TC_BK;
+        const int dy = tap / p.ksz - p.pad, dx = tap % p.ksz - p.pad;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx);
+        tma_load_4d(&map_a, &full_bar[s], st, c0, dx, y0 + dy, img);
+        uint8_t* bdst = st + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
+        const int wtap = p.flip_taps ? p.ksz * p.ksz - 1 - tap : tap;
+        tma_load_3d(&map_w, &full_bar[s], bdst, c0, n0, wtap);
+        if (SPLIT3) tma_load_3d(&map_wlo, &full_bar[s], bdst + b_bytes, c0, n0, wtap);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+        if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t ad = make_desc(a_addr + k * 32), bd = make_desc(b_addr + k * 32);
+          if (SPLIT3) {
+            const uint64_t ald = make_desc(a_addr + A_TILE_BYTES + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
+            tc_mma_tf32(tmem_base, ad, bld, idesc, (kb | k) != 0);      // hi * lo
+            tc_mma_tf32(tmem_base, ald, bd, idesc, 1);                  // lo * hi
+            tc_mma_tf32(tmem_base, ad, bd, idesc, 1);                   // hi * hi
+          } else {
+            tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          }
+        }
+        tc_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+      }
+      tc_commit(accum_bar);                  // accumulator complete -> epilogue
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = tile_m * TC_BM + row;
+    const bool mvalid = m < p.M;
+    float* yr = p.y + (size_t)m * p.y_cs;
+    const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
+    const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                        (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    for (int cb = 0; cb < p.BN; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+      if (!mvalid) continue;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int n = n0 + cb + g * 4;
+        if (n >= p.Cout) break;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int nn = n + e;
+          float x = __uint_as_float(v[g * 4 + e]);
+          if (nn < p.Cout) {
+            if (p.scale) x = x * __ldg(p.scale + nn);
+            if (p.shift) x = x + __ldg(p.shift + nn);
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (p.dropout) x = dr_hash_keep(p.drop_seed, p.drop_tag, (uint64_t)m * p.Cout + nn) ? x * 2.0f : 0.f;
+          }
+          o[e] = x;
+        }
+        if (vec_ok && n + 3 < p.Cout) {
+          if (rr) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rr + n);
+            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+          }
+          if (p.accumulate) {
+            const float4 y4 = *reinterpret_cast<const float4*>(yr + n);
+            o[0] += y4.x; o[1] += y4.y; o[2] += y4.z; o[3] += y4.w;
+          }
+          *reinterpret_cast<float4*>(yr + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int nn = n + e;
+            if (nn < p.Cout) {
+              float x = o[e];
+              if (rr) x += rr[nn];
+              if (p.accumulate) x += yr[nn];
+              yr[nn] = x;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (SPLIT3) {
+    // ===================== A splitter: hi = a & ~0x1fff (exact TF32), lo = a - hi =====================
+    const int t = threadIdx.x - 192;                      // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + A_TILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {  // elementwise: the swizzled layout is irrelevant
+        const int idx = i * 128 + t;
+        float4 a = a_hi[idx];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); l.x = a.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u); l.y = a.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); l.z = a.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u); l.w = a.w - h.w;
+        a_hi[idx] = h; a_lo[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      mbar_arrive(&split_bar[s]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so that the library does not link
+// libcuda.so (and therefore still loads on a CPU-only machine for the symbol / layer-table checks).
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+    else
+      fprintf(stderr, "densereg: cuTensorMapEncodeTiled not available; tensor-core path disabled\n");
+  }
+  return fn;
+}
+
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box) {
+  EncodeFn enc = get_encode();
+  if (!enc) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "densereg: cuTensorMapEncodeTiled failed with CUresult %d (rank %d)\n", (int)r, rank);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// Weight operands for the tensor-core path are K-major copies [tap][cout][cin] prepared by the engine (p.w points at
+// that copy when ConvProblem::w_kmajor is set).  Eligibility: stride 1, k in {1,3}, square power-of-two maps that tile
+// into whole rows (W <= 128, 128 % W == 0), input view 16 B aligned with Cin % 4 == 0 and at least one 32-wide k-block.
+bool conv_tc_eligible(const ConvProblem& p) {
+  if (!p.w_kmajor) return false;
+  if (p.stride != 1 || (p.k != 1 && p.k != 3)) return false;
+  if (p.H != p.W || p.Ho != p.H || p.Wo != p.W) return false;
+  if (p.W < 2 || p.W > 128 || (128 % p.W) != 0) return false;
+  if ((p.W * p.H) % 128 != 0 && 128 % (p.W * p.H) != 0) return false;
+  if (p.Cin % 4 != 0 || p.Cin < 16 || (p.x_cs % 4) != 0 || (reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.w_kmajor) & 15) != 0) return false;
+  if (p.Cout < 8) return false;
+  if (p.pad_t != (p.k - 1) / 2 || p.pad_l != p.pad_t) return false;
+  return true;
+}
+
+int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
+  static bool attr_set[2] = {false, false};
+  TcParams t;
+  t.M = p.B * p.H * p.W; t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t; t.flip_taps = p.flip_taps;
+  int BN = (p.Cout + 15) / 16 * 16;
+  if (BN > 256) BN = 256;
+  if (split3 && BN > 128) BN = 128;                        // 3xTF32 doubles the operand bytes per stage
+  t.BN = BN;
+  t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
+  int cols = 32; while (cols < BN) cols <<= 1;
+  t.tmem_cols = cols;
+  const int stage_bytes = (split3 ? 2 : 1) * (A_TILE_BYTES + BN * TC_BK * 4);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  const int num_kb = p.k * p.k * t.kblocks_per_tap;
+  if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
+  t.stages = stages;
+  t.y = p.y; t.y_cs = p.y_cs; t.scale = p.scale; t.shift = p.shift; t.relu = p.relu; t.res = p.res; t.res_cs = p.res_cs;
+  t.accumulate = p.accumulate; t.dropout = p.dropout; t.drop_seed = p.drop_seed; t.drop_tag = p.drop_tag;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (4 * stages + 2) * 8 + 1024 + 64;
+
+  // activation map: dims (C, W, H, B)
+  CUtensorMap ma, mw, mwlo;
+  const int rows = TC_BM / p.W;                            // image rows per tile (may exceed H -> several images)
+  const int bh = rows < p.H ? rows : p.H;
+  const int bb = rows < p.H ? 1 : rows / p.H;
+  cuuint64_t ad[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  cuuint64_t as[3] = {(cuuint64_t)p.x_cs * 4, (cuuint64_t)p.W * p.x_cs * 4, (cuuint64_t)p.H * p.W * p.x_cs * 4};
+  cuuint32_t ab[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.W, (cuuint32_t)bh, (cuuint32_t)bb};
+  if (!encode_map(&ma, p.x, 4, ad, as, ab)) return 0;
+  // weight map: dims (Cin, Cout, taps) over the K-major copy
+  cuuint64_t wd[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)(p.k * p.k)};
+  cuuint64_t ws[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
+  cuuint32_t wb[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
+  if (!encode_map(&mw, p.w_kmajor, 3, wd, ws, wb)) return 0;
+  mwlo = mw;
+  if (split3) { if (!encode_map(&mwlo, p.w_kmajor_lo, 3, wd, ws, wb)) return 0; }
+
+  dim3 grid((t.M + TC_BM - 1) / TC_BM, (p.Cout + BN - 1) / BN);
+  if (split3) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
+    conv_tc_kernel<true><<<grid, 320, smem_bytes, st>>>(ma, mw, mwlo, t);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+    conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
+  }
+  return 1;
+}

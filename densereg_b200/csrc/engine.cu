@@ -21,11 +21,11 @@ struct Layer {
   int k, stride, cin, cout, brn, relu;
   float wd;
   int64_t w_off, p_off, s_off;
-  int64_t aff_off, bstat_off, sum_off;
+  int64_t aff_off, bstat_off, sum_off, wk_off;
   int in_hw, out_hw;
 };
 
-struct LayerDev { int C, brn, kk, cin; long long w_off, p_off, s_off, aff_off; };
+struct LayerDev { int C, brn, kk, cin; long long w_off, p_off, s_off, aff_off, wk_off; };
 
 struct Buf { int H, W, C, Cs; size_t off; int raw; };   // Cs = padded channel stride; off in per-crop elements
 struct View { int buf = -1; int coff = 0; int C = 0; };
@@ -63,7 +63,10 @@ struct dr_handle {
   float *params = nullptr, *state = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
   // owned device memory
   float *act = nullptr, *gact = nullptr, *rawa = nullptr, *scratch = nullptr;
-  float *aff = nullptr, *bstat = nullptr, *wt = nullptr, *wdmask = nullptr;
+  float *aff = nullptr, *bstat = nullptr, *wdmask = nullptr;
+  // 16 B aligned weight copies: wk = K-major [tap][cout][cin], wa = plain [tap][cin][cout]; *_hi/_lo = exact-TF32 split (3xTF32)
+  float *wk = nullptr, *wa = nullptr, *wk_hi = nullptr, *wk_lo = nullptr, *wa_hi = nullptr, *wa_lo = nullptr;
+  size_t n_wk = 0;
   double *sums = nullptr, *sums_bw = nullptr, *loss_acc = nullptr;
   int32_t* clamp_dev = nullptr;
   LayerDev* ltab = nullptr;
@@ -72,6 +75,7 @@ struct dr_handle {
   int64_t launches = 0;
   std::string err;
   int precision = 0;
+  int64_t tc_launches = 0;
 };
 
 namespace {
@@ -120,6 +124,7 @@ struct Builder {
     L.aff_off = (int64_t)h->n_aff; h->n_aff += 2 * cout;
     L.bstat_off = (int64_t)h->n_bstat; h->n_bstat += 4 * cout;
     L.sum_off = (int64_t)h->n_sums; h->n_sums += 2 * cout;
+    L.wk_off = (int64_t)h->n_wk; h->n_wk += ((size_t)k * k * cin * cout + 3) / 4 * 4;
     h->layers.push_back(L);
     return (int)h->layers.size() - 1;
   }
@@ -283,15 +288,23 @@ __global__ void fold_all_kernel(const LayerDev* __restrict__ t, const float* __r
   }
 }
 
-// wt[(kk-1-tap)][n][c] = w[tap][c][n] for every layer (dgrad weights)
-__global__ void transpose_all_kernel(const LayerDev* __restrict__ t, const float* __restrict__ params, float* __restrict__ wt) {
+// per-layer aligned weight copies: wa[tap][c][n] = w, wk[tap][n][c] = w^T (K-major for the tensor-core path and the
+// SIMT dgrad); with split != 0 also the exact-TF32 hi / lo = w - hi parts of both.
+__global__ void prep_weights_kernel(const LayerDev* __restrict__ t, const float* __restrict__ params, float* __restrict__ wk,
+                                    float* __restrict__ wa, float* __restrict__ wk_hi, float* __restrict__ wk_lo,
+                                    float* __restrict__ wa_hi, float* __restrict__ wa_lo, int split) {
   const LayerDev L = t[blockIdx.x];
   const float* w = params + L.w_off;
-  float* o = wt + L.w_off;
   const size_t n = (size_t)L.kk * L.cin * L.C;
   for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) {
-    int c = (int)(i % L.cin); size_t r = i / L.cin; int n_o = (int)(r % L.C); int tap = (int)(r / L.C);
-    o[i] = w[((size_t)(L.kk - 1 - tap) * L.cin + c) * L.C + n_o];
+    const int n_o = (int)(i % L.C); const size_t r = i / L.C; const int c = (int)(r % L.cin); const int tap = (int)(r / L.cin);
+    const size_t ik = L.wk_off + ((size_t)tap * L.C + n_o) * L.cin + c;
+    const float v = w[i];
+    wa[L.wk_off + i] = v; wk[ik] = v;
+    if (split) {
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u), lo = v - hi;
+      wa_hi[L.wk_off + i] = hi; wa_lo[L.wk_off + i] = lo; wk_hi[ik] = hi; wk_lo[ik] = lo;
+    }
   }
 }
 
@@ -332,8 +345,46 @@ struct Exec {
 };
 
 int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
-  if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) return launch_conv_tc(p, precision == DR_PREC_TF32X3, st);
+  if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) {
+    int n = launch_conv_tc(p, precision == DR_PREC_TF32X3, st);
+    if (n > 0) { h->tc_launches += n; return n; }
+  }
   return launch_conv_simt(p, st);
+}
+
+// (re)build the aligned weight copies from the bound parameters; called once per forward pass
+int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
+  const size_t bytes = h->n_wk * sizeof(float);
+  if (!h->wk) {
+    CUDA_TRY(h, cudaMalloc(&h->wk, bytes)); CUDA_TRY(h, cudaMalloc(&h->wa, bytes)); h->ws_bytes += 2 * bytes;
+  }
+  const int split = precision == DR_PREC_TF32X3;
+  if (split && !h->wk_hi) {
+    CUDA_TRY(h, cudaMalloc(&h->wk_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wk_lo, bytes));
+    CUDA_TRY(h, cudaMalloc(&h->wa_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wa_lo, bytes)); h->ws_bytes += 4 * bytes;
+  }
+  prep_weights_kernel<<<dim3((unsigned)h->layers.size(), 8), 256, 0, st>>>(h->ltab, h->params, h->wk, h->wa, h->wk_hi, h->wk_lo,
+                                                                           h->wa_hi, h->wa_lo, split);
+  ++h->launches;
+  return DR_OK;
+}
+
+// weight operands of one conv for the forward pass / for dgrad
+void set_fwd_weights(dr_handle* h, const Layer& L, int precision, ConvProblem& p) {
+  p.w = h->params + L.w_off; p.flip_taps = 0;
+  if (precision != DR_PREC_FP32 && h->wk) {
+    const bool x3 = precision == DR_PREC_TF32X3;
+    p.w_kmajor = (x3 ? h->wk_hi : h->wk) + L.wk_off;
+    p.w_kmajor_lo = x3 ? h->wk_lo + L.wk_off : nullptr;
+  }
+}
+void set_dgrad_weights(dr_handle* h, const Layer& L, int precision, ConvProblem& p) {
+  p.w = h->wk + L.wk_off; p.flip_taps = 1;                 // rows (tap, cout), cin contiguous
+  if (precision != DR_PREC_FP32) {
+    const bool x3 = precision == DR_PREC_TF32X3;
+    p.w_kmajor = (x3 ? h->wa_hi : h->wa) + L.wk_off;        // K-major for dgrad: [tap][cin][cout]
+    p.w_kmajor_lo = x3 ? h->wa_lo + L.wk_off : nullptr;
+  }
 }
 
 int ensure_workspace(dr_handle* h, int B, bool train) {
@@ -353,8 +404,6 @@ int ensure_workspace(dr_handle* h, int B, bool train) {
     CUDA_TRY(h, cudaMalloc(&h->rawa, bytes)); h->ws_bytes += bytes;
     bytes = h->scratch_per_crop * cap * sizeof(float);
     CUDA_TRY(h, cudaMalloc(&h->scratch, bytes)); h->ws_bytes += bytes;
-    bytes = h->n_params * sizeof(float);
-    CUDA_TRY(h, cudaMalloc(&h->wt, bytes)); h->ws_bytes += bytes;
     h->cap_train = true;
   }
   h->cap_B = cap;
@@ -377,6 +426,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
   if (ud.n > 8) return fail(h, DR_ERR_UNSUPPORTED, "num_stack > 4 not supported");
   for (int i = 0; i < ud.n; ++i) { ud.p[i] = X.ptr(h->uvd_dst[i]); ud.cs[i] = X.cs(h->uvd_dst[i]); }
   nl += launch_make_uvd(B, IN, OUT, x0, tiny, ud, st);
+  if (training || h->precision != DR_PREC_FP32) { rc = prep_weights(h, h->precision, st); if (rc) return rc; }
   if (training) {
     CUDA_TRY(h, cudaMemsetAsync(h->sums, 0, h->n_sums * sizeof(double), st));
   } else {
@@ -391,7 +441,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         p.x = X.ptr(o.in); p.x_cs = X.cs(o.in);
         p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
         p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
-        p.w = h->params + L.w_off;
+        set_fwd_weights(h, L, h->precision, p);
         const float* aff = h->aff + L.aff_off;
         const float* res = o.res.buf >= 0 ? X.ptr(o.res) : nullptr;
         const int res_cs = o.res.buf >= 0 ? X.cs(o.res) : 0;
@@ -447,7 +497,6 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   const int OUT = h->cfg.out_hw, J = h->cfg.num_jnt, S = h->cfg.num_stack;
   CUDA_TRY(h, cudaMemsetAsync(h->sums_bw, 0, h->n_sums * sizeof(double), st));
   CUDA_TRY(h, cudaMemsetAsync(h->loss_acc, 0, 4 * sizeof(double), st));
-  transpose_all_kernel<<<dim3((unsigned)h->layers.size(), 8), 256, 0, st>>>(h->ltab, h->params, h->wt); ++nl;
   // loss + dL/d(outputs)
   LossArgs la; memset(&la, 0, sizeof(la));
   la.B = B; la.hw = OUT; la.J = J; la.S = S;
@@ -494,7 +543,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.x = dz; p.x_cs = dz_cs; p.B = B; p.H = L.out_hw; p.W = L.out_hw; p.Cin = L.cout;
           p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin; p.k = L.k; p.stride = 1;
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
-          p.w = h->wt + L.w_off;
+          set_dgrad_weights(h, L, h->precision, p);
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
           nl += run_conv(h, p, h->precision, st);
         }
@@ -536,7 +585,7 @@ int init_device(dr_handle* h) {
   std::vector<float> wdm(h->n_params, 0.f);
   for (size_t i = 0; i < h->layers.size(); ++i) {
     const Layer& L = h->layers[i];
-    tab[i] = LayerDev{L.cout, L.brn, L.k * L.k, L.cin, L.w_off, L.p_off, L.s_off, L.aff_off};
+    tab[i] = LayerDev{L.cout, L.brn, L.k * L.k, L.cin, L.w_off, L.p_off, L.s_off, L.aff_off, L.wk_off};
     if (L.wd > 0) for (int64_t j = 0; j < (int64_t)L.k * L.k * L.cin * L.cout; ++j) wdm[L.w_off + j] = L.wd;
   }
   CUDA_TRY(h, cudaMalloc(&h->ltab, tab.size() * sizeof(LayerDev)));
@@ -580,7 +629,7 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
 int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
-  cudaFree(h->wt); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
+  cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
   cudaFree(h->clamp_dev); cudaFree(h->ltab);
   delete h;
   return DR_OK;
@@ -605,6 +654,7 @@ int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, vo
 }
 
 int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
+int64_t dr_tc_launch_count(const dr_handle* h) { return h ? h->tc_launches : 0; }
 size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes : 0; }
 
 int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out) {
@@ -727,7 +777,8 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   ConvProblem p; memset(&p, 0, sizeof(p));
   p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
-  p.w = h->params + L.w_off; p.y = y; p.y_cs = L.cout;
+  if (precision != DR_PREC_FP32) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
+  set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout;
   h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
   CUDA_TRY(h, cudaPeekAtLastError());
   return DR_OK;
@@ -749,16 +800,12 @@ int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const floa
   }
   if (dx) {
     if (L.stride != 1) return fail(h, DR_ERR_UNSUPPORTED, "dgrad only for stride-1 convs (the stem conv has no input gradient)");
-    float* wt = nullptr;
-    CUDA_TRY(h, cudaMalloc(&wt, nw * sizeof(float)));
-    h->launches += launch_transpose_weights(L.k, L.cin, L.cout, h->params + L.w_off, wt, st);
+    { int rc = prep_weights(h, precision, st); if (rc) return rc; }
     ConvProblem p; memset(&p, 0, sizeof(p));
     p.x = dy; p.x_cs = L.cout; p.B = B; p.H = L.out_hw; p.W = L.out_hw; p.Cin = L.cout; p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin;
     p.k = L.k; p.stride = 1; p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, 1);
-    p.w = wt; p.y = dx; p.y_cs = L.cin;
+    set_dgrad_weights(h, L, precision, p); p.y = dx; p.y_cs = L.cin;
     h->launches += run_conv(h, p, precision, st);
-    CUDA_TRY(h, cudaStreamSynchronize(st));
-    cudaFree(wt);
   }
   CUDA_TRY(h, cudaPeekAtLastError());
   return DR_OK;

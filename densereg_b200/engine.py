@@ -169,5 +169,9 @@ class DenseRegEngine:
         return int(self.lib.dr_launch_count(self._h))
 
     @property
+    def tc_launch_count(self):
+        return int(self.lib.dr_tc_launch_count(self._h))
+
+    @property
     def workspace_bytes(self):
         return int(self.lib.dr_workspace_bytes(self._h))

@@ -153,6 +153,8 @@ DR_API int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int g
 
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 DR_API int64_t dr_launch_count(const dr_handle* h);
+/* how many of those were tcgen05 (tensor-core) conv kernels */
+DR_API int64_t dr_tc_launch_count(const dr_handle* h);
 
 /* activation workspace bytes currently allocated */
 DR_API size_t dr_workspace_bytes(const dr_handle* h);

@@ -61,3 +61,37 @@ def test_conv_forward_and_backward(setup, precision):
     tol = 2e-5 if precision == "fp32" else 2e-3
     bad = {k: v for k, v in rep.items() if max(v.values()) > tol}
     assert not bad, bad
+
+
+TC_LAYERS = ["stem/conv_2/c2", "stem/conv_2/skip", "stem/conv_4/c3", "s0/hg/n4/upper1/c2", "s0/hg/n3/upper1/c1", "s0/hg/n2/lower3/c1",
+             "s0/hg/n1/lower1/c2", "s0/hg/n1/upper1/c3", "s0/hm_out", "s0/um_res1/c1", "s0/um_res1/c2", "s0/um_comb/c2", "s0/um_full2", "s0/um_out",
+             "s0/um_res2/c3"]
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 4e-3), ("tf32x3", 2e-5)])
+@pytest.mark.parametrize("B", [2, 3])
+def test_conv_tensor_core_path(setup, precision, tol, B):
+    """tcgen05 implicit GEMM (TMA + TMEM) forward and dgrad vs the oracle conv.  tf32: one pass, inputs truncated to
+    10 mantissa bits (bar 4e-3 of the output scale); tf32x3: split hi/lo, fp32-class (bar 2e-5)."""
+    eng, net, p = setup
+    names = [l["name"] for l in eng.layers()]
+    rep = {}
+    for name in TC_LAYERS:
+        c = net.by_name[name]; li = names.index(name)
+        hw = eng.layers()[li]["in_hw"]
+        g = torch.Generator().manual_seed(li + 7)
+        x = torch.randn(B, hw, hw, c.cin, generator=g)
+        xr = x.clone().requires_grad_(True)
+        y_ref = oracle_conv(net, p, c, xr)
+        dy = torch.randn(y_ref.shape, generator=g)
+        y_ref.backward(dy)
+        t0 = eng.tc_launch_count
+        y = eng.debug_conv(li, cu(x), precision)
+        dx, _ = eng.debug_conv_bwd(li, cu(x), cu(dy), precision)
+        torch.cuda.synchronize()
+        rep[name] = dict(fwd=relerr(y.cpu().numpy(), y_ref.detach().numpy()), dgrad=relerr(dx.cpu().numpy(), xr.grad.numpy()),
+                         tc_launches=eng.tc_launch_count - t0)
+    dump("conv_tc_err_%s_B%d.json" % (precision, B), rep)
+    bad = {k: v for k, v in rep.items() if max(v["fwd"], v["dgrad"]) > tol}
+    assert not bad, bad
+    assert sum(v["tc_launches"] for v in rep.values()) >= len(TC_LAYERS), "tensor-core path was not taken"

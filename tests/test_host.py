@@ -1,0 +1,91 @@
+"""CPU tests of the host-side mirror (densereg_b200/model.py): flag surface, result-file format (fixture rows taken
+from the reference's exp/result/*.txt -- data, format only), lr schedule, batch sharding, and the N>1 data-parallel
+path on world-size-2 gloo: all-reduce(sum) of the flat gradient + identical Adam on every rank == single-process
+accumulation over the same micro-batches (model/train_multi_gpu.py:16-39 semantics)."""
+import os
+import re
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_flag_surface_matches_reference_defaults():
+    from densereg_b200.model import build_argparser
+    f = build_argparser().parse_args([])
+    # model/hourglass_um_crop_tiny.py:29-62
+    assert (f.num_gpus, f.batch_size, f.debug_level, f.sub_batch, f.pid, f.is_train, f.net_module, f.is_aug, f.dataset,
+            f.epoch, f.num_stack, f.num_fea, f.kernel_size) == (1, 40, 1, 5, 0, True, "um_v1", True, "nyu", 80, 2, 128, 3)
+    f = build_argparser().parse_args("--dataset icvl --batch_size 40 --num_stack 2 --num_fea 128 --is_train False".split())
+    assert f.dataset == "icvl" and f.is_train is False      # readme.md:19,36 string booleans
+
+
+def test_result_row_format_matches_reference_files():
+    from densereg_b200.model import format_result_row
+    jn = {"icvl": 16, "nyu": 14, "msra": 21}
+    for line in open(os.path.join(GOLD, "result_format_rows.txt")):
+        ds, row = line.split("|", 1)
+        name, *vals = row.rstrip("\n").split("\t")
+        assert len(vals) == 3 * jn[ds]
+        assert all(re.fullmatch(r"-?\d+\.\d{4}", v) for v in vals)
+        assert "/" not in name
+        # round trip through our writer reproduces the reference row byte for byte
+        assert format_result_row(name.replace("\\", "/"), [float(v) for v in vals]) == row
+
+
+def test_lr_schedule_and_sharding():
+    from densereg_b200.model import shard_batch
+    from oracle import um_v1_torch as U
+    assert U.lr_at(0, 100) == 1e-3 and abs(U.lr_at(100, 100) - 1e-4) < 1e-12 and abs(U.lr_at(250, 100) - 1e-5) < 1e-12
+    for world in (1, 2, 4, 8):
+        cover = []
+        for r in range(world):
+            lo, hi = shard_batch(64, r, world)
+            cover += list(range(lo, hi))
+        assert cover == list(range(64))
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from densereg_b200.model import allreduce_gradients, shard_batch
+    from densereg_b200 import synth
+    from oracle import um_v1_torch as U
+    torch.set_num_threads(2)
+    net = U.Net(1, 16, 4)
+    p, s = net.init_params(0, stddev=0.05), net.init_state()
+    dms, poses, cfgs, coms = synth.make_batch(2, 4, seed=3)
+    lo, hi = shard_batch(2, rank, world)
+    _, g, _ = U.loss_and_grads(net, p, s, dms[lo:hi, ..., 0], poses[lo:hi], cfgs[lo:hi], coms[lo:hi], dropout_seed=rank)
+    g = allreduce_gradients(g.clone(), world)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    U.adam_step(p, g, m, v, step=1, lr=1e-3, accum_steps=1, world=world)
+    if rank == 0:
+        torch.save(dict(p=p, g=g), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_data_parallel_world2_gloo_equals_accumulation(tmp_path):
+    import torch.multiprocessing as mp
+    from densereg_b200 import synth
+    from oracle import um_v1_torch as U
+    out = str(tmp_path / "rank0.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single process: accumulate the two shards as two micro-batches, divide by 2
+    net = U.Net(1, 16, 4)
+    p, s = net.init_params(0, stddev=0.05), net.init_state()
+    dms, poses, cfgs, coms = synth.make_batch(2, 4, seed=3)
+    gsum = torch.zeros_like(p)
+    for r in range(2):
+        _, g, _ = U.loss_and_grads(net, p, s.clone(), dms[r:r + 1, ..., 0], poses[r:r + 1], cfgs[r:r + 1], coms[r:r + 1], dropout_seed=r)
+        gsum += g
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    U.adam_step(p, gsum, m, v, step=1, lr=1e-3, accum_steps=2, world=1)
+    assert float((got["g"] - gsum).abs().max() / gsum.abs().max()) < 1e-5
+    assert float((got["p"] - p).abs().max()) < 1e-6
