@@ -214,14 +214,15 @@ def main():
     names = [l["name"] for l in eng.layers()]
     li = names.index("s0/um_comb/c2")
     xs = [torch.randn(B, 32, 32, 256, device=dev) for _ in range(4)]       # 4 x 42 MB inputs + outputs > 126 MB L2
+    yb = eng.debug_conv(li, xs[0], args.precision)
     for x in xs:
-        eng.debug_conv(li, x, args.precision)
+        eng.debug_conv(li, x, args.precision, reuse_weights=True, out=yb)
     torch.cuda.synchronize()
     reps = 12
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for r in range(reps):
-        eng.debug_conv(li, xs[r % 4], args.precision)
+        eng.debug_conv(li, xs[r % 4], args.precision, reuse_weights=True, out=yb)
     e1.record(); torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / reps
     k_flops = 2.0 * B * 1024 * 9 * 256 * 256

@@ -52,6 +52,8 @@ int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st);
 // tcgen05 path (conv_tc.cu). Returns 0 launches if the problem shape is not eligible.
 bool conv_tc_eligible(const ConvProblem& p);
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st);
+bool wgrad_tc_eligible(const WgradProblem& p);
+int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st);
 
 // ---- vote -----------------------------------------------------------------------------------
 int launch_vote(int B, int H, int W, int J,

@@ -302,7 +302,11 @@ __global__ void prep_weights_kernel(const LayerDev* __restrict__ t, const float*
     const float v = w[i];
     wa[L.wk_off + i] = v; wk[ik] = v;
     if (split) {
-      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u), lo = v - hi;
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+      const float lo = __uint_as_float(lb);
       wa_hi[L.wk_off + i] = hi; wa_lo[L.wk_off + i] = lo; wk_hi[ik] = hi; wk_lo[ik] = lo;
     }
   }
@@ -352,6 +356,14 @@ int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st)
   return launch_conv_simt(p, st);
 }
 
+int run_wgrad(dr_handle* h, const WgradProblem& p, int precision, cudaStream_t st) {
+  if (precision != DR_PREC_FP32 && wgrad_tc_eligible(p)) {
+    int n = launch_wgrad_tc(p, precision == DR_PREC_TF32X3, st);
+    if (n > 0) { h->tc_launches += n; return n; }
+  }
+  return launch_wgrad_simt(p, st);
+}
+
 // (re)build the aligned weight copies from the bound parameters; called once per forward pass
 int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
   const size_t bytes = h->n_wk * sizeof(float);
@@ -363,7 +375,7 @@ int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
     CUDA_TRY(h, cudaMalloc(&h->wk_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wk_lo, bytes));
     CUDA_TRY(h, cudaMalloc(&h->wa_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wa_lo, bytes)); h->ws_bytes += 4 * bytes;
   }
-  prep_weights_kernel<<<dim3((unsigned)h->layers.size(), 8), 256, 0, st>>>(h->ltab, h->params, h->wk, h->wa, h->wk_hi, h->wk_lo,
+  prep_weights_kernel<<<dim3((unsigned)h->layers.size(), 48), 256, 0, st>>>(h->ltab, h->params, h->wk, h->wa, h->wk_hi, h->wk_lo,
                                                                            h->wa_hi, h->wa_lo, split);
   ++h->launches;
   return DR_OK;
@@ -536,7 +548,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin; wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout;
         wp.k = L.k; wp.stride = L.stride; wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         wp.dw = h->grads + L.w_off;
-        nl += launch_wgrad_simt(wp, st);
+        nl += run_wgrad(h, wp, h->precision, st);
         if (o.need_dgrad) {
           nl += apply_fills(h, X, o.gw_in, st);
           ConvProblem p; memset(&p, 0, sizeof(p));
@@ -771,13 +783,14 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
 }
 
 int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {
+  const bool reuse = (precision & 0x100) != 0 && h && h->wk; precision &= 0xff;
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;
   if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
   const Layer& L = h->layers[layer];
   ConvProblem p; memset(&p, 0, sizeof(p));
   p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
-  if (precision != DR_PREC_FP32) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
+  if (precision != DR_PREC_FP32 && !reuse) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
   set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout;
   h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
   CUDA_TRY(h, cudaPeekAtLastError());
@@ -796,7 +809,7 @@ int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const floa
     wp.x = x; wp.x_cs = L.cin; wp.dy = dy; wp.dy_cs = L.cout; wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin;
     wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout; wp.k = L.k; wp.stride = L.stride;
     wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride); wp.dw = dw;
-    h->launches += launch_wgrad_simt(wp, st);
+    h->launches += run_wgrad(h, wp, precision, st);
   }
   if (dx) {
     if (L.stride != 1) return fail(h, DR_ERR_UNSUPPORTED, "dgrad only for stride-1 convs (the stem conv has no input gradient)");

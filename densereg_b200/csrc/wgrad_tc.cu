@@ -1,0 +1,234 @@
+// wgrad_tc.cu -- filter gradient on the tensor cores (sm_100a): dW[tap][cin][cout] += sum_pixels X_tap[pix][cin]^T * dY[pix][cout]
+// as a tcgen05 GEMM with BOTH operands MN-major (the reduction dimension -- pixels -- is the slow-moving index of the
+// NHWC tensors, so no transposition pass is needed).
+//
+// Replaces TF's Conv2DBackpropFilter for the stride-1 1x1 / 3x3 convs of network/um_v1.py (one third of the training FLOPs).
+//
+// Per CTA: D[128 cin, BN couts] (fp32 in TMEM) accumulates over a contiguous range of 32-pixel k-blocks of ONE filter tap:
+//   A = X^T : 4 TMA boxes (32 ch, bw, bh, bb) -- one per 32-channel chunk -- of the forward input at the tap's spatial offset
+//             (out-of-image pixels are TMA zero-fill = SAME padding); smem [chunk][32 pixels][32 floats], 128B-span swizzle with 32 B atoms
+//             (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B == UMMA SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit operands).
+//   B = dY  : BN/32 boxes of d(raw conv output), unshifted, same layout.
+//   4 MMAs (M=128, N=BN, K=8 pixels, kind::tf32, a_major = b_major = MN) per k-block; UMMA descriptors: LBO = 4096 B between
+//   32-wide chunks, SBO = 512 B between 4-pixel groups, start advanced by 1024 B per K=8 step.
+//   3xTF32 (DR_PREC_TF32X3): four splitter warps rewrite each landed stage in place into hi = rn_tf32(v) and lo = rn_tf32(v-hi)
+//   (A and B), 3 MMAs per k-step.
+// Epilogue: tcgen05.ld -> red.global.add.f32 into the flat gradient (split over pixel ranges across blockIdx.z, and micro-batch
+// accumulation, are both just "+=").
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int WG_KB = 32;                         // pixels per k-block
+constexpr int WG_CHUNK_BYTES = WG_KB * 128;       // one 32-channel chunk of one k-block: 4 KB
+constexpr int WG_A_BYTES = 4 * WG_CHUNK_BYTES;    // 128 cin
+
+struct WgParams {
+  int H, W, Cin, Cout, ksz, pad;
+  int BN, nchunks_b;
+  int total_kb, kb_per_split;
+  int cin_tiles;
+  int stages, tmem_cols;
+  int bw, bh, bb;
+  float* dw;
+};
+
+template <bool SPLIT3>
+__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.nchunks_b * WG_CHUNK_BYTES;
+  const int stage_bytes = (SPLIT3 ? 2 : 1) * (WG_A_BYTES + b_bytes);      // [A | B] (+ [A_lo | B_lo])
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* split_bar = empty_bar + p.stages;
+  uint64_t* accum_bar = split_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = blockIdx.x / p.cin_tiles;
+  const int c0 = (blockIdx.x - tap * p.cin_tiles) * 128;
+  const int n0 = blockIdx.y * p.BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.total_kb) kb_end = p.total_kb;
+  const int num_kb = kb_end - kb_begin;           // >= 1 by construction
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 128); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dy = tap / p.ksz - p.pad, dx = tap % p.ksz - p.pad;
+      const uint32_t tx = (uint32_t)(WG_A_BYTES + b_bytes);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int pix = (kb_begin + i) * WG_KB;
+        const int img = pix / (p.H * p.W);
+        const int rem = pix - img * p.H * p.W;
+        const int y = rem / p.W, x = rem - y * p.W;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_4d(&map_x, &full_bar[s], st + j * WG_CHUNK_BYTES, c0 + 32 * j, x + dx, y + dy, img);
+        for (int j = 0; j < p.nchunks_b; ++j)
+          tma_load_4d(&map_dy, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, n0 + 32 * j, x, y, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // a_format = b_format = TF32, c = F32, a_major = b_major = MN (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+        if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + WG_A_BYTES;
+        const uint32_t lo_off = (uint32_t)(WG_A_BYTES + b_bytes);
+#pragma unroll
+        for (int k = 0; k < WG_KB / 8; ++k) {
+          const uint64_t ad = make_desc_mn(a_addr + k * 1024, WG_CHUNK_BYTES, 512);
+          const uint64_t bd = make_desc_mn(b_addr + k * 1024, WG_CHUNK_BYTES, 512);
+          if (SPLIT3) {
+            const uint64_t ald = make_desc_mn(a_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
+            const uint64_t bld = make_desc_mn(b_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
+            tc_mma_tf32(tmem_base, ad, bld, idesc, (i | k) != 0);
+            tc_mma_tf32(tmem_base, ald, bd, idesc, 1);
+            tc_mma_tf32(tmem_base, ad, bd, idesc, 1);
+          } else {
+            tc_mma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(accum_bar);
+    }
+  } else if (warp < 6) {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int c = c0 + q * 32 + lane;                       // TMEM lane == cin row of the tile
+    const bool cvalid = c < p.Cin;
+    float* row = p.dw + ((size_t)tap * p.Cin + c) * p.Cout;
+    for (int cb = 0; cb < p.BN; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+      if (!cvalid) continue;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int n = n0 + cb + e;
+        if (n < p.Cout) atomicAdd(row + n, __uint_as_float(v[e]));
+      }
+    }
+    tc_fence_before();
+  } else if (SPLIT3) {
+    const int t = threadIdx.x - 192;
+    const int n16 = (WG_A_BYTES + b_bytes) / 16;             // float4 elements of [A | B]
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % p.stages;
+      const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + WG_A_BYTES + b_bytes);
+      for (int idx = t; idx < n16; idx += 128) {
+        float4 a = hi[idx], h, l;
+        h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
+        h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
+        h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
+        h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
+        hi[idx] = h; lo[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&split_bar[s]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+bool wgrad_tc_eligible(const WgradProblem& p) {
+  if (p.stride != 1 || (p.k != 1 && p.k != 3)) return false;
+  if (p.H != p.W || p.Ho != p.H || p.Wo != p.W) return false;
+  if (p.W < 8 || p.W > 128 || (p.W & (p.W - 1)) != 0) return false;
+  if (p.Cin % 4 != 0 || p.Cout % 4 != 0 || p.Cin < 16 || p.Cout < 16) return false;
+  if ((p.x_cs % 4) != 0 || (p.dy_cs % 4) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.dy) & 15) != 0) return false;
+  if (p.pad_t != (p.k - 1) / 2 || p.pad_l != p.pad_t) return false;
+  if ((long long)p.B * p.H * p.W < 2048) return false;       // too few pixels to amortise a tensor-core tile
+  return true;
+}
+
+int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
+  static bool attr_set[2] = {false, false};
+  WgParams t;
+  t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t;
+  int BN = (p.Cout + 31) / 32 * 32;
+  if (BN > 256) BN = 256;
+  if (split3 && BN > 128) BN = 128;
+  t.BN = BN; t.nchunks_b = BN / 32;
+  const long long M = (long long)p.B * p.H * p.W;
+  t.total_kb = (int)((M + WG_KB - 1) / WG_KB);
+  t.cin_tiles = (p.Cin + 127) / 128;
+  const int cout_tiles = (p.Cout + BN - 1) / BN;
+  const int tiles = t.cin_tiles * p.k * p.k * cout_tiles;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > t.total_kb / 8) splits = t.total_kb / 8;
+  if (splits < 1) splits = 1;
+  t.kb_per_split = (t.total_kb + splits - 1) / splits;
+  splits = (t.total_kb + t.kb_per_split - 1) / t.kb_per_split;
+  int cols = 32; while (cols < BN) cols <<= 1;
+  t.tmem_cols = cols;
+  const int stage_bytes = (split3 ? 2 : 1) * (WG_A_BYTES + t.nchunks_b * WG_CHUNK_BYTES);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  t.stages = stages;
+  t.bw = p.W < 32 ? p.W : 32;
+  t.bh = 32 / t.bw < p.H ? 32 / t.bw : p.H;
+  t.bb = 32 / (t.bw * t.bh);
+  t.dw = p.dw;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (4 * stages + 2) * 8 + 1024 + 64;
+
+  CUtensorMap mx, mdy;
+  cuuint32_t box[4] = {32, (cuuint32_t)t.bw, (cuuint32_t)t.bh, (cuuint32_t)t.bb};
+  cuuint64_t xd[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  cuuint64_t xs[3] = {(cuuint64_t)p.x_cs * 4, (cuuint64_t)p.W * p.x_cs * 4, (cuuint64_t)p.H * p.W * p.x_cs * 4};
+  if (!encode_map(&mx, p.x, 4, xd, xs, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 0;
+  cuuint64_t yd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  cuuint64_t ys[3] = {(cuuint64_t)p.dy_cs * 4, (cuuint64_t)p.W * p.dy_cs * 4, (cuuint64_t)p.H * p.W * p.dy_cs * 4};
+  if (!encode_map(&mdy, p.dy, 4, yd, ys, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 0;
+
+  dim3 grid(t.cin_tiles * p.k * p.k, cout_tiles, splits);
+  if (split3) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
+    wgrad_tc_kernel<true><<<grid, 320, smem_bytes, st>>>(mx, mdy, t);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+    wgrad_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(mx, mdy, t);
+  }
+  return 1;
+}

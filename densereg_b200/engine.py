@@ -82,6 +82,11 @@ class DenseRegEngine:
                             in_hw=li.in_hw, out_hw=li.out_hw))
         return out
 
+    def _layers_cached(self):
+        if not hasattr(self, "_layers"):
+            self._layers = self.layers()
+        return self._layers
+
     def init_params(self, seed=0, stddev=0.01):
         self._check(self.lib.dr_init_params(self._h, seed, stddev, self._stream()))
 
@@ -143,11 +148,12 @@ class DenseRegEngine:
     def optimizer_step(self, step, lr, accum_steps=1, world=1):
         self._check(self.lib.dr_optimizer_step(self._h, accum_steps, world, float(lr), int(step), self._stream()))
 
-    def debug_conv(self, layer, x, precision="fp32"):
-        L = self.layers()[layer]
+    def debug_conv(self, layer, x, precision="fp32", reuse_weights=False, out=None):
+        L = self._layers_cached()[layer]
         B = x.shape[0]
-        y = torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
-        self._check(self.lib.dr_debug_conv(self._h, layer, B, _ptr(x), _ptr(y), _ffi.PRECISIONS[precision], self._stream()))
+        y = out if out is not None else torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
+        self._check(self.lib.dr_debug_conv(self._h, layer, B, _ptr(x), _ptr(y), _ffi.PRECISIONS[precision] | (0x100 if reuse_weights else 0),
+                                           self._stream()))
         return y
 
     def debug_conv_bwd(self, layer, x, dy, precision="fp32", want_dx=True):

@@ -68,11 +68,11 @@ TC_LAYERS = ["stem/conv_2/c2", "stem/conv_2/skip", "stem/conv_4/c3", "s0/hg/n4/u
              "s0/um_res2/c3"]
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32", 4e-3), ("tf32x3", 2e-5)])
-@pytest.mark.parametrize("B", [2, 3])
+@pytest.mark.parametrize("precision,tol", [("tf32", 4e-3), ("tf32x3", 6e-5)])
+@pytest.mark.parametrize("B", [2, 5])
 def test_conv_tensor_core_path(setup, precision, tol, B):
     """tcgen05 implicit GEMM (TMA + TMEM) forward and dgrad vs the oracle conv.  tf32: one pass, inputs truncated to
-    10 mantissa bits (bar 4e-3 of the output scale); tf32x3: split hi/lo, fp32-class (bar 2e-5)."""
+    10 mantissa bits (bar 4e-3 of the output scale); tf32x3: split hi/lo, fp32-class (bar 6e-5: the tensor core's fp32 accumulation truncates, ~2e-5 at K=2304)."""
     eng, net, p = setup
     names = [l["name"] for l in eng.layers()]
     rep = {}
@@ -87,11 +87,15 @@ def test_conv_tensor_core_path(setup, precision, tol, B):
         y_ref.backward(dy)
         t0 = eng.tc_launch_count
         y = eng.debug_conv(li, cu(x), precision)
-        dx, _ = eng.debug_conv_bwd(li, cu(x), cu(dy), precision)
+        pr = p.clone().requires_grad_(True)
+        oracle_conv(net, pr, c, x).backward(dy)
+        dx, dw = eng.debug_conv_bwd(li, cu(x), cu(dy), precision)
         torch.cuda.synchronize()
+        nw = c.k * c.k * c.cin * c.cout
         rep[name] = dict(fwd=relerr(y.cpu().numpy(), y_ref.detach().numpy()), dgrad=relerr(dx.cpu().numpy(), xr.grad.numpy()),
+                         wgrad=relerr(dw.cpu().numpy(), pr.grad[c.w_off:c.w_off + nw].numpy()),
                          tc_launches=eng.tc_launch_count - t0)
     dump("conv_tc_err_%s_B%d.json" % (precision, B), rep)
-    bad = {k: v for k, v in rep.items() if max(v["fwd"], v["dgrad"]) > tol}
+    bad = {k: v for k, v in rep.items() if max(v["fwd"], v["dgrad"], v["wgrad"]) > tol}
     assert not bad, bad
     assert sum(v["tc_launches"] for v in rep.values()) >= len(TC_LAYERS), "tensor-core path was not taken"

@@ -24,8 +24,9 @@ for _ in range(a.iters):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+y = eng.debug_conv(li, x, a.precision)
 for _ in range(10):
-    eng.debug_conv(li, x, a.precision)
+    eng.debug_conv(li, x, a.precision, reuse_weights=True, out=y)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 fl = 2.0 * a.batch * l["out_hw"] ** 2 * l["k"] ** 2 * l["cin"] * l["cout"]

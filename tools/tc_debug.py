@@ -27,11 +27,16 @@ for name in names:
     torch.cuda.synchronize()
     err = (y - ref).abs().max().item() / ref.abs().max().item()
     dy = torch.randn_like(ref)
-    dx, _ = eng.debug_conv_bwd(li, x, dy, prec)
+    t1 = eng.tc_launch_count
+    dx, dw = eng.debug_conv_bwd(li, x, dy, prec)
     torch.cuda.synchronize()
+    nbw = eng.tc_launch_count - t1
+    xr = x.permute(0, 3, 1, 2)
+    dwr = torch.nn.grad.conv2d_weight(xr, (cout, cin, k, k), dy.permute(0, 3, 1, 2).contiguous(), padding=k // 2).permute(2, 3, 1, 0).reshape(-1)
+    werr = (dw - dwr).abs().max().item() / dwr.abs().max().item()
     dref = F.conv_transpose2d(dy.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
     derr = (dx - dref).abs().max().item() / dref.abs().max().item()
-    print(" fwd relerr %.2e  dgrad relerr %.2e  tc_launches %d" % (err, derr, eng.tc_launch_count - t0), flush=True)
+    print(" fwd %.2e  dgrad %.2e  wgrad %.2e  tc fwd/bwd launches %d/%d" % (err, derr, werr, t1 - t0, nbw), flush=True)
     if err > 1e-2:
         d = (y - ref).abs()
         idx = torch.nonzero(d > 1e-2 * ref.abs().max())[:5]
