@@ -241,6 +241,20 @@ __global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ r
   }
 }
 
+// float4 variant: C % 4 == 0, all strides % 4 == 0, all bases 16 B aligned; 32-bit index math
+__global__ void brn_apply_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ raw, unsigned raw_cs4,
+                                    const float4* __restrict__ aff, int relu, const float4* __restrict__ res, unsigned res_cs4,
+                                    float4* __restrict__ y, unsigned y_cs4) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / C4, c = i - pix * C4;
+    const float4 x = raw[(size_t)pix * raw_cs4 + c], a = __ldg(aff + c), b = __ldg(aff + C4 + c);
+    float4 v = make_float4(fmaf(x.x, a.x, b.x), fmaf(x.y, a.y, b.y), fmaf(x.z, a.z, b.z), fmaf(x.w, a.w, b.w));
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (res) { const float4 r = res[(size_t)pix * res_cs4 + c]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    y[(size_t)pix * y_cs4 + c] = v;
+  }
+}
+
 __global__ void brn_bwd_reduce_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ raw,
                                       int raw_cs, const float* __restrict__ aff, const float* __restrict__ bstat, int relu,
                                       double* __restrict__ sums) {
@@ -289,6 +303,53 @@ __global__ void brn_bwd_apply_kernel(size_t npix, int C, const float* __restrict
       gparam[c] += (float)sums[c];
       gparam[C + c] += (float)((double)r * sums[C + c] + (double)d * sums[c]);
     }
+  }
+}
+
+__global__ void brn_bwd_apply_v4_kernel(unsigned n4, unsigned C4, unsigned npix, const float4* __restrict__ dy, unsigned dy_cs4,
+                                        const float4* __restrict__ raw, unsigned raw_cs4, const float* __restrict__ aff,
+                                        const float* __restrict__ bstat, const float* __restrict__ bg, int relu,
+                                        const double* __restrict__ sums, float4* __restrict__ draw, unsigned draw_cs4,
+                                        float* __restrict__ gparam) {
+  const int C = (int)C4 * 4;
+  const double inv_n = 1.0 / (double)npix;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / C4, cq = i - pix * C4;
+    const float4 x4 = raw[(size_t)pix * raw_cs4 + cq], g4 = dy[(size_t)pix * dy_cs4 + cq];
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    float gs[4] = {g4.x, g4.y, g4.z, g4.w}, o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = (int)cq * 4 + e;
+      const float sa = __ldg(aff + c), sb = __ldg(aff + C + c), mean = __ldg(bstat + c), inv_std = __ldg(bstat + C + c), r = __ldg(bstat + 2 * C + c);
+      const float gamma = __ldg(bg + C + c);
+      float g = gs[e];
+      if (relu && !(xs[e] * sa + sb > 0.f)) g = 0.f;
+      const float xh = (xs[e] - mean) * inv_std;
+      const float mg = (float)(sums[c] * inv_n), mgx = (float)(sums[C + c] * inv_n);
+      o[e] = gamma * r * inv_std * (g - mg - xh * mgx);
+    }
+    draw[(size_t)pix * draw_cs4 + cq] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float r = bstat[2 * C + c], d = bstat[3 * C + c];
+      gparam[c] += (float)sums[c];
+      gparam[C + c] += (float)((double)r * sums[C + c] + (double)d * sums[c]);
+    }
+  }
+}
+
+// float4 copy / accumulate of a view (optional depth mask)
+__global__ void copy_view_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ src, unsigned src_cs4, float4* __restrict__ dst,
+                                    unsigned dst_cs4, int accumulate, const float* __restrict__ tiny_mask) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / C4, c = i - pix * C4;
+    float4 v = src[(size_t)pix * src_cs4 + c];
+    if (tiny_mask && tiny_mask[pix] < -0.9f) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* o = dst + (size_t)pix * dst_cs4 + c;
+    if (accumulate) { const float4 w = *o; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    *o = v;
   }
 }
 
@@ -469,7 +530,13 @@ int launch_upadd_bwd_lo(int B, int H, int W, int C, const float* dy, int dy_cs, 
 }
 int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* dst, int dst_cs, int accumulate,
                      const float* tiny_mask, cudaStream_t st) {
-  copy_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, src, src_cs, dst, dst_cs, accumulate, tiny_mask);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (C % 4 == 0 && src_cs % 4 == 0 && dst_cs % 4 == 0 && al(src) && al(dst) && npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
+    const unsigned n4 = (unsigned)(npix * (C / 4));
+    copy_view_v4_kernel<<<blocks_for(n4), EW_T, 0, st>>>(n4, C / 4, (const float4*)src, src_cs / 4, (float4*)dst, dst_cs / 4, accumulate, tiny_mask);
+  } else {
+    copy_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, src, src_cs, dst, dst_cs, accumulate, tiny_mask);
+  }
   return 1;
 }
 int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st) {
@@ -499,7 +566,15 @@ int launch_fold_affine(int C, int brn, const float* pb, const float* state, floa
 }
 int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
                      const float* res, int res_cs, float* y, int y_cs, cudaStream_t st) {
-  brn_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (C % 4 == 0 && raw_cs % 4 == 0 && y_cs % 4 == 0 && (!res || res_cs % 4 == 0) && al(raw) && al(y) && al(aff) && (!res || al(res)) &&
+      npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
+    const unsigned n4 = (unsigned)(npix * (C / 4));
+    brn_apply_v4_kernel<<<blocks_for(n4), EW_T, 0, st>>>(n4, C / 4, (const float4*)raw, raw_cs / 4, (const float4*)aff, relu,
+                                                        (const float4*)res, res_cs / 4, (float4*)y, y_cs / 4);
+  } else {
+    brn_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
+  }
   return 1;
 }
 int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
@@ -510,8 +585,15 @@ int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const 
 int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                          const float* aff, const float* bstat, const float* beta_gamma, int relu,
                          const double* sums, float* draw, int draw_cs, float* gparam, cudaStream_t st) {
-  brn_bwd_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, beta_gamma, relu,
-                                                              sums, draw, draw_cs, gparam);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (C % 4 == 0 && raw_cs % 4 == 0 && dy_cs % 4 == 0 && draw_cs % 4 == 0 && al(raw) && al(dy) && al(draw) && npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
+    const unsigned n4 = (unsigned)(npix * (C / 4));
+    brn_bwd_apply_v4_kernel<<<blocks_for(n4), EW_T, 0, st>>>(n4, C / 4, (unsigned)npix, (const float4*)dy, dy_cs / 4, (const float4*)raw,
+                                                            raw_cs / 4, aff, bstat, beta_gamma, relu, sums, (float4*)draw, draw_cs / 4, gparam);
+  } else {
+    brn_bwd_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, beta_gamma, relu,
+                                                                sums, draw, draw_cs, gparam);
+  }
   return 1;
 }
 int launch_bias_bwd(size_t npix, int C, const float* dy, int dy_cs, const float* out, int out_cs, int relu, int dropout,

@@ -10,11 +10,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def make(S, F, J, B, seed, stddev, training=True):
+def make(S, F, J, B, seed, stddev, training=True, precision="fp32"):
     from densereg_b200.engine import DenseRegEngine
     from densereg_b200 import synth
     from oracle import um_v1_torch as U
-    eng = DenseRegEngine(num_stack=S, num_fea=F, num_jnt=J, max_batch=B, training=training)
+    eng = DenseRegEngine(num_stack=S, num_fea=F, num_jnt=J, max_batch=B, training=training, precision=precision)
     net = U.Net(S, F, J)
     p, s = net.init_params(seed, stddev=stddev), net.init_state()
     eng.load_flat(p, s)
@@ -22,10 +22,11 @@ def make(S, F, J, B, seed, stddev, training=True):
     return eng, net, p, s, data
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 2), (2, 128, 16, 2), (2, 128, 21, 1)])
-def test_forward_eval_matches_oracle(built_lib, S, F, J, B):
+def test_forward_eval_matches_oracle(built_lib, S, F, J, B, precision):
     from oracle import vote_numpy as V
-    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 3, 0.05, training=False)
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 3, 0.05, training=False, precision=precision)
     x0 = torch.from_numpy(V.norm_dm(dms[..., 0], coms)[..., None])
     hms, hm3s, ums = net.forward(p, s, x0, training=False)
     out = eng.forward(cu(dms), cu(coms))
@@ -34,8 +35,10 @@ def test_forward_eval_matches_oracle(built_lib, S, F, J, B):
         rep["hm%d" % st] = relerr(out["hm_outs"][st].cpu().numpy(), hms[st].numpy())
         rep["hm3%d" % st] = relerr(out["hm3_outs"][st].cpu().numpy(), hm3s[st].numpy())
         rep["um%d" % st] = relerr(out["um_outs"][st].cpu().numpy(), ums[st].numpy())
-    dump("net_eval_err_S%dF%dJ%d.json" % (S, F, J), rep)
-    assert max(rep.values()) < 1e-4, rep
+    rep["tc_launches"] = eng.tc_launch_count
+    dump("net_eval_err_S%dF%dJ%d_%s.json" % (S, F, J, precision), rep)
+    assert max(v for k, v in rep.items() if k != "tc_launches") < 1e-4, rep
+    assert (eng.tc_launch_count > 0) == (precision != "fp32")
 
 
 def test_layerwise_trace_eval(built_lib):
@@ -87,13 +90,14 @@ def test_net_golden_statistics_on_gpu(built_lib):
     assert relerr(out["um_outs"][0].cpu().numpy()[0, ::4, ::4], g["um_sub"]) < 1e-4
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 3), (2, 128, 14, 2)])
-def test_infer_end_to_end(built_lib, S, F, J, B):
+def test_infer_end_to_end(built_lib, S, F, J, B, precision):
     """crops -> xyz mm through dr_infer vs oracle forward + oracle vote.  The vote given IDENTICAL maps is
     index-exact (test_gpu_vote); end to end the maps differ by fp32 summation order, so top-5 lists are
     compared where the oracle's 5th/6th score margin exceeds the map error, and xyz at 1e-3 mm on those joints."""
     from oracle import vote_numpy as V
-    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 7, 0.05, training=False)
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 7, 0.05, training=False, precision=precision)
     x0n = V.norm_dm(dms[..., 0], coms)
     hms, hm3s, ums = net.forward(p, s, torch.from_numpy(x0n[..., None]), training=False)
     d32 = V.tiny_dm(x0n)
@@ -107,7 +111,7 @@ def test_infer_end_to_end(built_lib, S, F, J, B):
     safe = margin > 1e-4 * np.abs(R).max()
     same = (top5 == ref_top5).all(-1)
     err = np.abs(xyz - ref_xyz).reshape(B, J, 3).max(-1)
-    dump("infer_e2e_S%dF%dJ%d.json" % (S, F, J), dict(frac_same_top5=float(same.mean()), frac_safe=float(safe.mean()),
+    dump("infer_e2e_S%dF%dJ%d_%s.json" % (S, F, J, precision), dict(frac_same_top5=float(same.mean()), frac_safe=float(safe.mean()),
                                                      max_err_mm_same=float(np.nanmax(np.where(same, err, 0))),
                                                      mean_joint_err_mm=float(np.nanmean(np.linalg.norm((xyz - ref_xyz).reshape(B, J, 3), axis=-1)))))
     assert same[safe].all()
@@ -115,10 +119,11 @@ def test_infer_end_to_end(built_lib, S, F, J, B):
     assert (err[fin] <= 1e-3 * max(1.0, float(np.abs(ref_xyz[np.isfinite(ref_xyz)]).max()) / 100.0)).all()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("S,F,J,B", [(1, 64, 16, 2), (2, 128, 16, 2)])
-def test_training_step_matches_oracle(built_lib, S, F, J, B):
+def test_training_step_matches_oracle(built_lib, S, F, J, B, precision):
     from oracle import um_v1_torch as U
-    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 11, 0.05, training=True)
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 11, 0.05, training=True, precision=precision)
     s_ref = s.clone()
     L, g_ref, outs = U.loss_and_grads(net, p, s_ref, dms[..., 0], poses, cfgs, coms, dropout_seed=5)
     # training-mode forward outputs
@@ -165,12 +170,16 @@ def test_training_step_matches_oracle(built_lib, S, F, J, B):
     U.adam_step(p_ref, g_ref.clone(), m, v, step=1, lr=1e-3, accum_steps=1, world=1)
     eng.optimizer_step(step=1, lr=1e-3, accum_steps=1, world=1)
     rep["adam_max_abs"] = float(np.abs(eng.params.cpu().numpy() - p_ref.numpy()).max())
-    dump("train_err_S%dF%dJ%d.json" % (S, F, J), dict(rep, per_layer=per))
+    rep["tc_launches"] = eng.tc_launch_count
+    dump("train_err_S%dF%dJ%d_%s.json" % (S, F, J, precision), dict(rep, per_layer=per))
     assert rep["fwd_um_last"] < 2e-4 and rep["fwd_hm_last"] < 2e-4, rep
     assert rep["loss"] < 1e-4, rep
-    assert per["s%d/um_out" % (S - 1)] < 1e-5, rep          # no ReLU between the loss and this layer: exact to fp32
+    assert per["s%d/um_out" % (S - 1)] < (1e-5 if precision == "fp32" else 1e-4), rep   # no ReLU between the loss and this layer
     assert gpu_total <= 3 * noise_total + 3e-4, rep
-    assert worst_ratio <= 4.0, rep
+    if precision == "fp32":
+        assert worst_ratio <= 4.0, rep
+    else:       # the split-TF32 path's ~1e-5 conv error flips a few more ReLU decisions than fp32 does: cap per-layer error instead
+        assert rep["grad_worst"] < 5e-2, rep
     assert rep["state"] < 1e-4, rep
     # clip makes the first Adam step +-lr for almost all weights; differences only where g is ~0
     assert rep["adam_max_abs"] <= 2.1e-3, rep
