@@ -24,9 +24,11 @@ struct ConvProblem {
   int Ho, Wo, Cout;
   int k, stride, pad_t, pad_l;
   const float* w;          // [k*k*Cin][Cout] row-major (TF HWIO flattened)
+  int w_ld;                // row length of w in floats (0 = Cout); the dgrad copy has rows padded to 4 floats
   int flip_taps;           // read weight taps in reverse order (dgrad == conv with the 180-degree rotated filter)
   const float* w_kmajor;   // tensor-core path: 16 B aligned K-major copy [tap][Cout][Cin] (hi part for 3xTF32), or null
   const float* w_kmajor_lo;// 3xTF32: lo part
+  int wk_ld;               // row length (floats, multiple of 4) of the K-major copy: Cin rounded up to 4
   float* y; int y_cs;      // output view
   // epilogue: v = acc*scale[n] + shift[n]; relu; dropout; + res; + beta*y_old
   const float* scale;      // may be null (=1)
@@ -77,6 +79,9 @@ int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* ds
                      const float* tiny_mask, cudaStream_t st);
 int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st);
 int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums /*2C, pre-zeroed*/, cudaStream_t st);
+// stats + finalize in ONE launch (last block finalizes); counter must be zero on entry
+int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, double* sums, unsigned int* counter,
+                                  const float* beta_gamma, float* state, float* aff, float* bstat, int update_state, cudaStream_t st);
 // BRN finalize (train): sums -> mean/var, r, d, affine a,b; optional state update. bstat: mean,inv_std,r,d [C each]
 int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
                         float* aff, float* bstat, int update_state, cudaStream_t st);

@@ -53,7 +53,8 @@ conv_fwd_kernel(ConvProblem p) {
   // ---- B-load mapping: float4 along n when Cout%4==0 (checked at run time per element group) ----
   const int b_n = (tid & 15) * 4;       // 16 threads x 4 = 64 columns
   const int b_k = tid >> 4;             // 16 rows
-  const bool b_vec = (p.Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
+  const int w_ld = p.w_ld ? p.w_ld : p.Cout;
+  const bool b_vec = (w_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
 
   float acc[8][4];
 #pragma unroll
@@ -88,7 +89,7 @@ conv_fwd_kernel(ConvProblem p) {
     if (kb < K) {
       int kbs = kb;
       if (p.flip_taps) { int tp = kb / p.Cin; kbs = (p.k * p.k - 1 - tp) * p.Cin + (kb - tp * p.Cin); }
-      const float* wr = p.w + (size_t)kbs * p.Cout + n0 + b_n;
+      const float* wr = p.w + (size_t)kbs * w_ld + n0 + b_n;
       if (b_vec && n0 + b_n + 3 < p.Cout) {
         float4 v = __ldg(reinterpret_cast<const float4*>(wr));
         b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;

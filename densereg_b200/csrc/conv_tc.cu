@@ -222,14 +222,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // Weight operands for the tensor-core path are K-major copies [tap][cout][cin] prepared by the engine (p.w points at
 // that copy when ConvProblem::w_kmajor is set).  Eligibility: stride 1, k in {1,3}, square power-of-two maps that tile
-// into whole rows (W <= 128, 128 % W == 0), input view 16 B aligned with Cin % 4 == 0 and at least one 32-wide k-block.
+// into whole rows (W <= 128, 128 % W == 0), input view 16 B aligned with a channel stride that is a multiple of 4 floats (Cin itself may be ragged: 131, 65, 515 ...;
+// TMA zero-fills the channel tail of both operands).
 bool conv_tc_eligible(const ConvProblem& p) {
   if (!p.w_kmajor) return false;
   if (p.stride != 1 || (p.k != 1 && p.k != 3)) return false;
   if (p.H != p.W || p.Ho != p.H || p.Wo != p.W) return false;
   if (p.W < 2 || p.W > 128 || (128 % p.W) != 0) return false;
   if ((p.W * p.H) % 128 != 0 && 128 % (p.W * p.H) != 0) return false;
-  if (p.Cin % 4 != 0 || p.Cin < 16 || (p.x_cs % 4) != 0 || (reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;
+  if (p.Cin < 8 || (p.x_cs % 4) != 0 || (reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;   // only STRIDES must be 16 B multiples
+  if (p.wk_ld < p.Cin || (p.wk_ld % 4) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.w_kmajor) & 15) != 0) return false;
   if (p.Cout < 8) return false;
   if (p.pad_t != (p.k - 1) / 2 || p.pad_l != p.pad_t) return false;
@@ -268,7 +270,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   if (!encode_map(&ma, p.x, 4, ad, as, ab)) return 0;
   // weight map: dims (Cin, Cout, taps) over the K-major copy
   cuuint64_t wd[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)(p.k * p.k)};
-  cuuint64_t ws[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
+  cuuint64_t ws[2] = {(cuuint64_t)p.wk_ld * 4, (cuuint64_t)p.wk_ld * p.Cout * 4};
   cuuint32_t wb[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
   if (!encode_map(&mw, p.w_kmajor, 3, wd, ws, wb)) return 0;
   mwlo = mw;

@@ -21,11 +21,11 @@ struct Layer {
   int k, stride, cin, cout, brn, relu;
   float wd;
   int64_t w_off, p_off, s_off;
-  int64_t aff_off, bstat_off, sum_off, wk_off;
+  int64_t aff_off, bstat_off, sum_off, wk_off, wa_off;   // wk: [tap][cout][cin_p], wa: [tap][cin][cout_p] (inner dims padded to 4)
   int in_hw, out_hw;
 };
 
-struct LayerDev { int C, brn, kk, cin; long long w_off, p_off, s_off, aff_off, wk_off; };
+struct LayerDev { int C, brn, kk, cin; long long w_off, p_off, s_off, aff_off, wk_off, wa_off; };
 
 struct Buf { int H, W, C, Cs; size_t off; int raw; };   // Cs = padded channel stride; off in per-crop elements
 struct View { int buf = -1; int coff = 0; int C = 0; };
@@ -66,8 +66,9 @@ struct dr_handle {
   float *aff = nullptr, *bstat = nullptr, *wdmask = nullptr;
   // 16 B aligned weight copies: wk = K-major [tap][cout][cin], wa = plain [tap][cin][cout]; *_hi/_lo = exact-TF32 split (3xTF32)
   float *wk = nullptr, *wa = nullptr, *wk_hi = nullptr, *wk_lo = nullptr, *wa_hi = nullptr, *wa_lo = nullptr;
-  size_t n_wk = 0;
+  size_t n_wk = 0, n_wa = 0;
   double *sums = nullptr, *sums_bw = nullptr, *loss_acc = nullptr;
+  unsigned int* counters = nullptr;      // one per layer: last-block-done counters of the fused stats+finalize kernel
   int32_t* clamp_dev = nullptr;
   LayerDev* ltab = nullptr;
   int cap_B = 0; bool cap_train = false;
@@ -124,7 +125,8 @@ struct Builder {
     L.aff_off = (int64_t)h->n_aff; h->n_aff += 2 * cout;
     L.bstat_off = (int64_t)h->n_bstat; h->n_bstat += 4 * cout;
     L.sum_off = (int64_t)h->n_sums; h->n_sums += 2 * cout;
-    L.wk_off = (int64_t)h->n_wk; h->n_wk += ((size_t)k * k * cin * cout + 3) / 4 * 4;
+    L.wk_off = (int64_t)h->n_wk; h->n_wk += (size_t)k * k * cout * ((cin + 3) / 4 * 4);
+    L.wa_off = (int64_t)h->n_wa; h->n_wa += (size_t)k * k * cin * ((cout + 3) / 4 * 4);
     h->layers.push_back(L);
     return (int)h->layers.size() - 1;
   }
@@ -296,18 +298,20 @@ __global__ void prep_weights_kernel(const LayerDev* __restrict__ t, const float*
   const LayerDev L = t[blockIdx.x];
   const float* w = params + L.w_off;
   const size_t n = (size_t)L.kk * L.cin * L.C;
+  const int cin_p = (L.cin + 3) / 4 * 4, cout_p = (L.C + 3) / 4 * 4;
   for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) {
     const int n_o = (int)(i % L.C); const size_t r = i / L.C; const int c = (int)(r % L.cin); const int tap = (int)(r / L.cin);
-    const size_t ik = L.wk_off + ((size_t)tap * L.C + n_o) * L.cin + c;
+    const size_t ik = L.wk_off + ((size_t)tap * L.C + n_o) * cin_p + c;
+    const size_t ia = L.wa_off + ((size_t)tap * L.cin + c) * cout_p + n_o;
     const float v = w[i];
-    wa[L.wk_off + i] = v; wk[ik] = v;
+    wa[ia] = v; wk[ik] = v;
     if (split) {
       uint32_t hb, lb;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
       const float hi = __uint_as_float(hb);
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
       const float lo = __uint_as_float(lb);
-      wa_hi[L.wk_off + i] = hi; wa_lo[L.wk_off + i] = lo; wk_hi[ik] = hi; wk_lo[ik] = lo;
+      wa_hi[ia] = hi; wa_lo[ia] = lo; wk_hi[ik] = hi; wk_lo[ik] = lo;
     }
   }
 }
@@ -366,14 +370,17 @@ int run_wgrad(dr_handle* h, const WgradProblem& p, int precision, cudaStream_t s
 
 // (re)build the aligned weight copies from the bound parameters; called once per forward pass
 int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
-  const size_t bytes = h->n_wk * sizeof(float);
-  if (!h->wk) {
-    CUDA_TRY(h, cudaMalloc(&h->wk, bytes)); CUDA_TRY(h, cudaMalloc(&h->wa, bytes)); h->ws_bytes += 2 * bytes;
+  const size_t bk = h->n_wk * sizeof(float), ba = h->n_wa * sizeof(float);
+  if (!h->wk) {      // pad elements are zeroed once here and never written again
+    CUDA_TRY(h, cudaMalloc(&h->wk, bk)); CUDA_TRY(h, cudaMalloc(&h->wa, ba)); h->ws_bytes += bk + ba;
+    CUDA_TRY(h, cudaMemsetAsync(h->wk, 0, bk, st)); CUDA_TRY(h, cudaMemsetAsync(h->wa, 0, ba, st));
   }
   const int split = precision == DR_PREC_TF32X3;
   if (split && !h->wk_hi) {
-    CUDA_TRY(h, cudaMalloc(&h->wk_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wk_lo, bytes));
-    CUDA_TRY(h, cudaMalloc(&h->wa_hi, bytes)); CUDA_TRY(h, cudaMalloc(&h->wa_lo, bytes)); h->ws_bytes += 4 * bytes;
+    CUDA_TRY(h, cudaMalloc(&h->wk_hi, bk)); CUDA_TRY(h, cudaMalloc(&h->wk_lo, bk));
+    CUDA_TRY(h, cudaMalloc(&h->wa_hi, ba)); CUDA_TRY(h, cudaMalloc(&h->wa_lo, ba)); h->ws_bytes += 2 * (bk + ba);
+    CUDA_TRY(h, cudaMemsetAsync(h->wk_hi, 0, bk, st)); CUDA_TRY(h, cudaMemsetAsync(h->wk_lo, 0, bk, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->wa_hi, 0, ba, st)); CUDA_TRY(h, cudaMemsetAsync(h->wa_lo, 0, ba, st));
   }
   prep_weights_kernel<<<dim3((unsigned)h->layers.size(), 48), 256, 0, st>>>(h->ltab, h->params, h->wk, h->wa, h->wk_hi, h->wk_lo,
                                                                            h->wa_hi, h->wa_lo, split);
@@ -383,19 +390,21 @@ int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
 
 // weight operands of one conv for the forward pass / for dgrad
 void set_fwd_weights(dr_handle* h, const Layer& L, int precision, ConvProblem& p) {
-  p.w = h->params + L.w_off; p.flip_taps = 0;
+  p.w = h->params + L.w_off; p.w_ld = L.cout; p.flip_taps = 0;
   if (precision != DR_PREC_FP32 && h->wk) {
     const bool x3 = precision == DR_PREC_TF32X3;
-    p.w_kmajor = (x3 ? h->wk_hi : h->wk) + L.wk_off;
+    p.w_kmajor = (x3 ? h->wk_hi : h->wk) + L.wk_off;        // [tap][cout][cin_p]
     p.w_kmajor_lo = x3 ? h->wk_lo + L.wk_off : nullptr;
+    p.wk_ld = (L.cin + 3) / 4 * 4;
   }
 }
 void set_dgrad_weights(dr_handle* h, const Layer& L, int precision, ConvProblem& p) {
-  p.w = h->wk + L.wk_off; p.flip_taps = 1;                 // rows (tap, cout), cin contiguous
+  p.w = h->wk + L.wk_off; p.w_ld = (L.cin + 3) / 4 * 4; p.flip_taps = 1;   // rows (tap, cout), cin contiguous (padded)
   if (precision != DR_PREC_FP32) {
     const bool x3 = precision == DR_PREC_TF32X3;
-    p.w_kmajor = (x3 ? h->wa_hi : h->wa) + L.wk_off;        // K-major for dgrad: [tap][cin][cout]
-    p.w_kmajor_lo = x3 ? h->wa_lo + L.wk_off : nullptr;
+    p.w_kmajor = (x3 ? h->wa_hi : h->wa) + L.wa_off;        // K-major for dgrad: [tap][cin][cout_p]
+    p.w_kmajor_lo = x3 ? h->wa_lo + L.wa_off : nullptr;
+    p.wk_ld = (L.cout + 3) / 4 * 4;
   }
 }
 
@@ -441,6 +450,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
   if (training || h->precision != DR_PREC_FP32) { rc = prep_weights(h, h->precision, st); if (rc) return rc; }
   if (training) {
     CUDA_TRY(h, cudaMemsetAsync(h->sums, 0, h->n_sums * sizeof(double), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, h->layers.size() * sizeof(unsigned int), st));
   } else {
     fold_all_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state, h->aff); ++nl;
   }
@@ -462,9 +472,8 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
           p.y = X.ptr(rv); p.y_cs = X.cs(rv);
           nl += run_conv(h, p, h->precision, st);
           double* sums = h->sums + L.sum_off;
-          nl += launch_channel_stats(X.npix(rv), L.cout, p.y, p.y_cs, sums, st);
-          nl += launch_brn_finalize(L.cout, (double)X.npix(rv), sums, h->params + L.p_off, h->state + L.s_off,
-                                    h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
+          nl += launch_channel_stats_finalize(X.npix(rv), L.cout, p.y, p.y_cs, sums, h->counters + o.layer, h->params + L.p_off,
+                                              h->state + L.s_off, h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
           nl += launch_brn_apply(X.npix(rv), L.cout, p.y, p.y_cs, aff, L.relu, res, res_cs, X.ptr(o.out), X.cs(o.out), st);
         } else {
           p.y = X.ptr(o.out); p.y_cs = X.cs(o.out);
@@ -597,7 +606,7 @@ int init_device(dr_handle* h) {
   std::vector<float> wdm(h->n_params, 0.f);
   for (size_t i = 0; i < h->layers.size(); ++i) {
     const Layer& L = h->layers[i];
-    tab[i] = LayerDev{L.cout, L.brn, L.k * L.k, L.cin, L.w_off, L.p_off, L.s_off, L.aff_off, L.wk_off};
+    tab[i] = LayerDev{L.cout, L.brn, L.k * L.k, L.cin, L.w_off, L.p_off, L.s_off, L.aff_off, L.wk_off, L.wa_off};
     if (L.wd > 0) for (int64_t j = 0; j < (int64_t)L.k * L.k * L.cin * L.cout; ++j) wdm[L.w_off + j] = L.wd;
   }
   CUDA_TRY(h, cudaMalloc(&h->ltab, tab.size() * sizeof(LayerDev)));
@@ -607,6 +616,7 @@ int init_device(dr_handle* h) {
   CUDA_TRY(h, cudaMalloc(&h->sums, h->n_sums * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->sums_bw, h->n_sums * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->loss_acc, 4 * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->counters, h->layers.size() * sizeof(unsigned int)));
   CUDA_TRY(h, cudaMalloc(&h->clamp_dev, sizeof(int32_t)));
   CUDA_TRY(h, cudaMemcpy(h->ltab, tab.data(), tab.size() * sizeof(LayerDev), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->wdmask, wdm.data(), wdm.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -642,7 +652,7 @@ int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
   cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
-  cudaFree(h->clamp_dev); cudaFree(h->ltab);
+  cudaFree(h->clamp_dev); cudaFree(h->ltab); cudaFree(h->counters);
   delete h;
   return DR_OK;
 }

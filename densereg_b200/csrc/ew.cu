@@ -178,22 +178,21 @@ __global__ void channel_stats_kernel(size_t npix, int C, const float* __restrict
 }
 
 // state layout per BRN conv: mov_mean[C], mov_var[C], biased_mean[C], biased_var[C], r_max, d_max, curr_t, local_step
-__global__ void brn_finalize_kernel(int C, double n, const double* __restrict__ sums, const float* __restrict__ bg,
-                                    float* __restrict__ state, float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
-  const float eps = 0.001f, decay = 0.99f;
+__device__ void brn_finalize_dev(int tid, int nthreads, int C, double n, const double* __restrict__ sums, const float* __restrict__ bg,
+                                 float* __restrict__ state, float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
+  const float eps = 0.001f, one_minus_decay = 0.01f;           // um_v1.py:9-10 (decay 0.99, epsilon 1e-3)
   const float r_max = state[4 * C], d_max = state[4 * C + 1], t = state[4 * C + 2], step = state[4 * C + 3];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double mean_d = sums[c] / n;
-    double var_d = sums[C + c] / n - mean_d * mean_d;
+  for (int c = tid; c < C; c += nthreads) {
+    double mean_d = __ldcg(sums + c) / n;
+    double var_d = __ldcg(sums + C + c) / n - mean_d * mean_d;
     if (var_d < 0) var_d = 0;
     float mean = (float)mean_d, var = (float)var_d;
     float mov_mean = state[c], mov_var = state[C + c];
     float stdv = sqrtf(var + eps), mov_std = sqrtf(mov_var + eps);
     float r = fminf(fmaxf(stdv / mov_std, 1.0f / r_max), r_max);               // ops.py:158-159
     float d = fminf(fmaxf((mean - mov_mean) / mov_std, -d_max), d_max);       // ops.py:161-162
-    float inv_std = rsqrtf(var + eps);
-    inv_std = 1.0f / sqrtf(var + eps);
+    float inv_std = 1.0f / sqrtf(var + eps);
     float beta = bg[c], gamma = bg[C + c];
     // y = ((x-mean)*inv_std*r + d)*gamma + beta = x*a + b
     float a = inv_std * r * gamma;
@@ -202,19 +201,54 @@ __global__ void brn_finalize_kernel(int C, double n, const double* __restrict__ 
     bstat[c] = mean; bstat[C + c] = inv_std; bstat[2 * C + c] = r; bstat[3 * C + c] = d;
     if (update_state) {                                                       // ops.py:134-137, zero-debiased EMA
       float bm = state[2 * C + c], bv = state[3 * C + c];
-      bm -= (bm - mean) * (1.0f - decay);
-      bv -= (bv - var) * (1.0f - decay);
-      float corr = 1.0f - powf(decay, step + 1.0f);
+      bm -= (bm - mean) * one_minus_decay;
+      bv -= (bv - var) * one_minus_decay;
+      float corr = 1.0f - powf(0.99f, step + 1.0f);
       state[2 * C + c] = bm; state[3 * C + c] = bv;
       state[c] = bm / corr; state[C + c] = bv / corr;
     }
   }
   __syncthreads();
-  if (update_state && threadIdx.x == 0) {
+  if (update_state && tid == 0) {
     state[4 * C] = 3.0f / (1.0f + 2.0f * expf(-t));                          // ops.py:141-144
     state[4 * C + 1] = 5.0f / (5000.0f * expf(-2.0f * t));                   // ops.py:146-149
     state[4 * C + 2] = t + 1e-5f;                                             // ops.py:151-153
     state[4 * C + 3] = step + 1.0f;
+  }
+}
+
+__global__ void brn_finalize_kernel(int C, double n, const double* __restrict__ sums, const float* __restrict__ bg,
+                                    float* __restrict__ state, float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
+  brn_finalize_dev(threadIdx.x, blockDim.x, C, n, sums, bg, state, aff, bstat, update_state);
+}
+
+// per-channel sum / sum of squares in double + BRN finalize by the LAST block to finish (one launch instead of two)
+__global__ void channel_stats_finalize_kernel(size_t npix, int C, const float* __restrict__ x, int x_cs, double* __restrict__ sums,
+                                              unsigned int* __restrict__ counter, const float* __restrict__ bg, float* __restrict__ state,
+                                              float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
+  __shared__ double s1[8][33], s2[8][33];
+  __shared__ int is_last;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
+      float v = x[p * x_cs + c];
+      a += (double)v; b += (double)v * (double)v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(sums + c, a); atomicAdd(sums + C + c, b);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    brn_finalize_dev(threadIdx.y * 32 + threadIdx.x, 256, C, (double)npix, sums, bg, state, aff, bstat, update_state);
   }
 }
 
@@ -553,6 +587,12 @@ static dim3 stats_grid(size_t npix, int C) {
 }
 int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums, cudaStream_t st) {
   channel_stats_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums);
+  return 1;
+}
+int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, double* sums, unsigned int* counter,
+                                  const float* beta_gamma, float* state, float* aff, float* bstat, int update_state, cudaStream_t st) {
+  channel_stats_finalize_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums, counter, beta_gamma, state, aff, bstat,
+                                                                            update_state);
   return 1;
 }
 int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
