@@ -38,6 +38,10 @@ struct ConvProblem {
   int accumulate;          // y = v + y_old
   int dropout;             // apply keep/2x after relu
   uint64_t drop_seed; uint32_t drop_tag;
+  // tensor-core path only: fused BRN batch statistics of the RAW conv output + finalize by the last CTA (all null = off)
+  double* stats;           // [2*Cout] sum / sum of squares (pre-zeroed)
+  unsigned int* stats_counter;   // pre-zeroed
+  const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
 };
 
 struct WgradProblem {

@@ -13,18 +13,19 @@
 //   B tile: 3-D TMA box (32 ch, BN couts, 1 tap) of the K-major weight copy [tap][cout][cin]; channels past Cin
 //           and couts past Cout are zero-filled.
 //   Both K-major, SWIZZLE_128B (32 fp32 = 128 B rows, 8-row 1024 B atoms): UMMA smem descriptors advance
-//   32 B per K=8 MMA.  DR_PREC_TF32X3: a split warpgroup rewrites each landed A tile into hi (13 low mantissa bits
-//   cleared) + lo = a - hi, the weights are pre-split, and every k-step issues hi*lo + lo*hi + hi*hi into the
-//   same TMEM accumulator (fp32-class accuracy; algorithmic FLOPs unchanged).
+//   32 B per K=8 MMA.  DR_PREC_TF32X3: four splitter warps rewrite each landed A tile in shared memory into
+//   hi = rn_tf32(v) and lo = rn_tf32(v - hi), the weights arrive pre-split (two TMA boxes), and every k-step issues hi*lo + lo*hi + hi*hi into the same TMEM accumulator (fp32-class accuracy; algorithmic FLOPs unchanged).
 // Warp roles (192 / 320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
-//   (TMEM lane quarter = warp_idx % 4), warps 6-9 A splitter (3xTF32 only).  mbarrier full/empty ring.
+//   (TMEM lane quarter = warp_idx % 4), warps 6-9 operand splitter (3xTF32 only).  mbarrier full/empty ring.
 #include "tc_common.cuh"
+#include "brn.cuh"
 
 namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // fp32 elements per k-block = one 128 B swizzle row
 constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4; // 16 KB
+constexpr int SPLIT_THREADS = 128;             // 4 splitter warps (3xTF32); 8 measured slower (issue-slot pressure on the MMA thread)
 
 struct TcParams {
   int M;                 // B*H*W output pixels
@@ -40,13 +41,14 @@ struct TcParams {
   const float* scale; const float* shift; int relu;
   const float* res; int res_cs; int accumulate;
   int dropout; unsigned long long drop_seed; unsigned int drop_tag;
+  double* stats; unsigned int* stats_counter; const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
 };
 
 using namespace tc;
 
 // dynamic smem layout (1024 B aligned): [stage][A hi 16K | (A lo 16K) | B hi BN*128 | (B lo BN*128)] ... barriers ... tmem ptr
 template <bool SPLIT3>
-__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+__global__ void __launch_bounds__(SPLIT3 ? 192 + SPLIT_THREADS : 192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,7 +66,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 128); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], SPLIT_THREADS / 32); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -83,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int pix0 = tile_m * TC_BM;
       const int img = pix0 / (p.H * p.W);
       const int y0 = (pix0 - img * p.H * p.W) / p.W;
-      const uint32_t tx = (uint32_t)(A_TILE_BYTES + (SPLIT3 ? 2 : 1) * b_bytes);
+      const uint32_t tx = (uint32_t)(A_TILE_BYTES + (SPLIT3 ? 2 : 1) * b_bytes);   // A fp32 (split in smem); B hi (+ lo, pre-split)
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
@@ -129,7 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp < 6) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait(accum_bar, 0);
+    mbar_wait_sleep(accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -139,9 +141,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
     const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    __shared__ float s_sum[4][256], s_sq[4][256];
+    __shared__ int s_last;
     for (int cb = 0; cb < p.BN; cb += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+      if (p.stats) {
+        // column sums over this warp's 32 rows by recursive halving: 31 shuffles, lane l ends with column cb+l
+        float a[32], b2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(v[i]); b2[i] = a[i] * a[i]; }   // rows past M are exact zeros
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          const bool up = (lane & sft) != 0;
+#pragma unroll
+          for (int j = 0; j < sft; ++j) {
+            const float sa = up ? a[j] : a[j + sft], ka = up ? a[j + sft] : a[j];
+            const float sb = up ? b2[j] : b2[j + sft], kb2 = up ? b2[j + sft] : b2[j];
+            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, sft);
+            b2[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, sft);
+          }
+        }
+        s_sum[q][cb + lane] = a[0]; s_sq[q][cb + lane] = b2[0];
+      }
       if (!mvalid) continue;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -184,29 +206,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
+    if (p.stats) {
+      const int et = q * 32 + lane;                                     // 0..127 (warps 2..5 -> q = 2,3,0,1)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < p.BN; col += 128) {
+        const int n = n0 + col;
+        if (n < p.Cout) {
+          atomicAdd(p.stats + n, (double)((s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col])));
+          atomicAdd(p.stats + p.Cout + n, (double)((s_sq[0][col] + s_sq[1][col]) + (s_sq[2][col] + s_sq[3][col])));
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) s_last = (atomicAdd(p.stats_counter, 1u) == gridDim.x * gridDim.y - 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {                                                     // last CTA: BRN finalize for the whole layer
+        __threadfence();
+        brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
+      }
+    }
     tc_fence_before();
   } else if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
-    const int t = threadIdx.x - 192;                      // 0..127
+    const int t = threadIdx.x - 192;                      // 0..SPLIT_THREADS-1
+    const int na4 = A_TILE_BYTES / 16, nb4 = 0;          // weights arrive pre-split (hi, lo) by TMA; only the A tile is split here
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % p.stages;
       const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
       mbar_wait(&full_bar[s], ph);
       float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-      float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + A_TILE_BYTES);
-#pragma unroll
-      for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {  // elementwise: the swizzled layout is irrelevant
-        const int idx = i * 128 + t;
-        float4 a = a_hi[idx];
+      float4* a_lo = a_hi + na4;
+      float4* b_hi = a_lo + na4;
+      float4* b_lo = b_hi + b_bytes / 16;
+      for (int idx = t; idx < na4 + nb4; idx += SPLIT_THREADS) {   // elementwise: the swizzled layout is irrelevant
+        float4* hp = idx < na4 ? a_hi + idx : b_hi + (idx - na4);
+        float4* lp = idx < na4 ? a_lo + idx : b_lo + (idx - na4);
+        const float4 a = *hp;
         float4 h, l;
         h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
         h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
         h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
         h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
-        a_hi[idx] = h; a_lo[idx] = l;
+        *hp = h; *lp = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-      mbar_arrive(&split_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);                       // one arrival per splitter warp
     }
   }
 
@@ -244,20 +289,23 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   t.M = p.B * p.H * p.W; t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t; t.flip_taps = p.flip_taps;
   int BN = (p.Cout + 15) / 16 * 16;
   if (BN > 256) BN = 256;
-  if (split3 && BN > 128) BN = 128;                        // 3xTF32 doubles the operand bytes per stage
+  if (split3 && BN > 128) BN = 128;                        // 3 stages of [A hi|lo, B hi|lo] fit; 2 stages at BN=256 measured slower
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
   int cols = 32; while (cols < BN) cols <<= 1;
   t.tmem_cols = cols;
   const int stage_bytes = (split3 ? 2 : 1) * (A_TILE_BYTES + BN * TC_BK * 4);
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (208 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
   if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
   t.stages = stages;
   t.y = p.y; t.y_cs = p.y_cs; t.scale = p.scale; t.shift = p.shift; t.relu = p.relu; t.res = p.res; t.res_cs = p.res_cs;
   t.accumulate = p.accumulate; t.dropout = p.dropout; t.drop_seed = p.drop_seed; t.drop_tag = p.drop_tag;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (4 * stages + 2) * 8 + 1024 + 64;
+  t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
+  t.bn_update_state = p.bn_update_state;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (4 * stages + 2) * 8 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
 
   // activation map: dims (C, W, H, B)
   CUtensorMap ma, mw, mwlo;
@@ -278,10 +326,10 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
 
   dim3 grid((t.M + TC_BM - 1) / TC_BM, (p.Cout + BN - 1) / BN);
   if (split3) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
-    conv_tc_kernel<true><<<grid, 320, smem_bytes, st>>>(ma, mw, mwlo, t);
+    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[1] = true; }
+    conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[0] = true; }
     conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
   }
   return 1;

@@ -375,7 +375,7 @@ int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
     CUDA_TRY(h, cudaMalloc(&h->wk, bk)); CUDA_TRY(h, cudaMalloc(&h->wa, ba)); h->ws_bytes += bk + ba;
     CUDA_TRY(h, cudaMemsetAsync(h->wk, 0, bk, st)); CUDA_TRY(h, cudaMemsetAsync(h->wa, 0, ba, st));
   }
-  const int split = precision == DR_PREC_TF32X3;
+  const int split = precision == DR_PREC_TF32X3;   // weights are pre-split (hi/lo) here; activations are split in shared memory
   if (split && !h->wk_hi) {
     CUDA_TRY(h, cudaMalloc(&h->wk_hi, bk)); CUDA_TRY(h, cudaMalloc(&h->wk_lo, bk));
     CUDA_TRY(h, cudaMalloc(&h->wa_hi, ba)); CUDA_TRY(h, cudaMalloc(&h->wa_lo, ba)); h->ws_bytes += 2 * (bk + ba);
@@ -470,10 +470,17 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         if (training && L.brn) {
           View rv = X.whole(o.raw);
           p.y = X.ptr(rv); p.y_cs = X.cs(rv);
-          nl += run_conv(h, p, h->precision, st);
           double* sums = h->sums + L.sum_off;
-          nl += launch_channel_stats_finalize(X.npix(rv), L.cout, p.y, p.y_cs, sums, h->counters + o.layer, h->params + L.p_off,
-                                              h->state + L.s_off, h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
+          const bool fuse = h->precision != DR_PREC_FP32 && conv_tc_eligible(p);
+          if (fuse) {          // statistics + finalize fused into the tcgen05 conv epilogue
+            p.stats = sums; p.stats_counter = h->counters + o.layer; p.bn_bg = h->params + L.p_off; p.bn_state = h->state + L.s_off;
+            p.bn_aff = h->aff + L.aff_off; p.bn_bstat = h->bstat + L.bstat_off; p.bn_update_state = update_state;
+          }
+          const int64_t tc_before = h->tc_launches;
+          nl += run_conv(h, p, h->precision, st);
+          if (!fuse || h->tc_launches == tc_before)      // SIMT path (or a failed tensor-map encode): separate statistics pass
+            nl += launch_channel_stats_finalize(X.npix(rv), L.cout, p.y, p.y_cs, sums, h->counters + o.layer, h->params + L.p_off,
+                                                h->state + L.s_off, h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
           nl += launch_brn_apply(X.npix(rv), L.cout, p.y, p.y_cs, aff, L.relu, res, res_cs, X.ptr(o.out), X.cs(o.out), st);
         } else {
           p.y = X.ptr(o.out); p.y_cs = X.cs(o.out);
@@ -501,7 +508,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
     }
   }
   h->launches += nl;
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -593,7 +600,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
     }
   }
   h->launches += nl;
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -668,7 +675,7 @@ int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, vo
   for (const Op& o : h->ops) {
     if (o.kind == OP_CONV && o.layer == layer) {
       h->launches += launch_gather_outputs(X.npix(o.out), o.out.C, grad ? X.gptr(o.out) : X.ptr(o.out), X.cs(o.out), dst, X.st);
-      CUDA_TRY(h, cudaPeekAtLastError());
+      CUDA_TRY(h, cudaGetLastError());
       return DR_OK;
     }
   }
@@ -702,14 +709,14 @@ int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   h->launches += launch_init_trunc_normal(h->n_params, h->params, stddev, seed, st);
   init_state_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state); ++h->launches;
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
 int dr_norm_dm(dr_handle* h, int B, int hw, const float* dm_mm, const float* coms, float* out, void* stream) {
   if (!h || !dm_mm || !coms || !out || B < 1 || hw < 1) return DR_ERR_ARG;
   h->launches += launch_norm_dm(B, hw, dm_mm, coms, out, (cudaStream_t)stream);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -731,7 +738,7 @@ int dr_forward(dr_handle* h, int B, const float* dm_mm, const float* coms,
   int rc = forward_impl(h, B, dm_mm, coms, is_training, update_state, dropout_seed, st);
   if (rc) return rc;
   copy_outputs(h, B, hm, hm3, um, st);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -744,7 +751,7 @@ int dr_vote(dr_handle* h, int B, int H, int W, int J,
   cudaStream_t st = (cudaStream_t)stream;
   if (clamp_count) CUDA_TRY(h, cudaMemsetAsync(clamp_count, 0, sizeof(int32_t), st));
   h->launches += launch_vote(B, H, W, J, hm, J, hm3, J, um, 3 * J, dm_norm, cfgs, coms, xyz_mm, top5_idx, clamp_count, st);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -759,7 +766,7 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
   h->launches += launch_vote(B, OUT, OUT, J, X.ptr(h->v_hm[s]), X.cs(h->v_hm[s]), X.ptr(h->v_hm3[s]), X.cs(h->v_hm3[s]),
                              X.ptr(h->v_um[s]), X.cs(h->v_um[s]), X.ptr(X.whole(h->buf_tiny)), cfgs, coms, xyz_mm, top5_idx,
                              h->clamp_dev, st);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -788,7 +795,7 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step)));
   h->launches += launch_adam(h->n_params, h->params, h->grads, h->adam_m, h->adam_v, 1.0f / (float)(accum_steps * world), 0.2f,
                              lr_t, (float)b1, (float)b2, 1e-8f, (cudaStream_t)stream);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -803,7 +810,7 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   if (precision != DR_PREC_FP32 && !reuse) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
   set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout;
   h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
@@ -830,7 +837,7 @@ int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const floa
     set_dgrad_weights(h, L, precision, p); p.y = dx; p.y_cs = L.cin;
     h->launches += run_conv(h, p, precision, st);
   }
-  CUDA_TRY(h, cudaPeekAtLastError());
+  CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 

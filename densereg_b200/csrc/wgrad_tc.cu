@@ -11,7 +11,7 @@
 //   B = dY  : BN/32 boxes of d(raw conv output), unshifted, same layout.
 //   4 MMAs (M=128, N=BN, K=8 pixels, kind::tf32, a_major = b_major = MN) per k-block; UMMA descriptors: LBO = 4096 B between
 //   32-wide chunks, SBO = 512 B between 4-pixel groups, start advanced by 1024 B per K=8 step.
-//   3xTF32 (DR_PREC_TF32X3): four splitter warps rewrite each landed stage in place into hi = rn_tf32(v) and lo = rn_tf32(v-hi)
+//   3xTF32 (DR_PREC_TF32X3): eight splitter warps rewrite each landed stage in place into hi = rn_tf32(v) and lo = rn_tf32(v-hi)
 //   (A and B), 3 MMAs per k-step.
 // Epilogue: tcgen05.ld -> red.global.add.f32 into the flat gradient (split over pixel ranges across blockIdx.z, and micro-batch
 // accumulation, are both just "+=").
@@ -24,6 +24,7 @@ namespace {
 constexpr int WG_KB = 32;                         // pixels per k-block
 constexpr int WG_CHUNK_BYTES = WG_KB * 128;       // one 32-channel chunk of one k-block: 4 KB
 constexpr int WG_A_BYTES = 4 * WG_CHUNK_BYTES;    // 128 cin
+constexpr int WG_SPLIT_THREADS = 256;             // 8 splitter warps (3xTF32)
 
 struct WgParams {
   int H, W, Cin, Cout, ksz, pad;
@@ -36,7 +37,7 @@ struct WgParams {
 };
 
 template <bool SPLIT3>
-__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+__global__ void __launch_bounds__(SPLIT3 ? 192 + WG_SPLIT_THREADS : 192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -58,7 +59,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int num_kb = kb_end - kb_begin;           // >= 1 by construction
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 128); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], WG_SPLIT_THREADS / 32); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,7 +123,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       tc_commit(accum_bar);
     }
   } else if (warp < 6) {
-    mbar_wait(accum_bar, 0);
+    mbar_wait_sleep(accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3;
     const int c = c0 + q * 32 + lane;                       // TMEM lane == cin row of the tile
@@ -148,7 +149,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_wait(&full_bar[s], ph);
       float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + WG_A_BYTES + b_bytes);
-      for (int idx = t; idx < n16; idx += 128) {
+      for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
         float4 a = hi[idx], h, l;
         h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
         h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
@@ -157,7 +158,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         hi[idx] = h; lo[idx] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&split_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
     }
   }
 
@@ -203,7 +205,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   int cols = 32; while (cols < BN) cols <<= 1;
   t.tmem_cols = cols;
   const int stage_bytes = (split3 ? 2 : 1) * (WG_A_BYTES + t.nchunks_b * WG_CHUNK_BYTES);
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (208 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   t.stages = stages;
@@ -224,10 +226,10 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
 
   dim3 grid(t.cin_tiles * p.k * p.k, cout_tiles, splits);
   if (split3) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
-    wgrad_tc_kernel<true><<<grid, 320, smem_bytes, st>>>(mx, mdy, t);
+    if (!attr_set[1]) { cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[1] = true; }
+    wgrad_tc_kernel<true><<<grid, 192 + WG_SPLIT_THREADS, smem_bytes, st>>>(mx, mdy, t);
   } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+    if (!attr_set[0]) { cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[0] = true; }
     wgrad_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(mx, mdy, t);
   }
   return 1;
