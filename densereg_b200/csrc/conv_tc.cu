@@ -34,6 +34,7 @@ struct TcParams {
   int ksz, pad;          // 1 or 3; pad (before)
   int flip_taps;         // dgrad: weight tap index reversed (180-degree rotation)
   int BN;                // N tile (multiple of 16, <= 256)
+  int tiles_m, tiles_n;  // persistent tile walk
   int kblocks_per_tap;   // ceil(Cin / 32)
   int stages;
   int tmem_cols;         // power of two >= BN, >= 32
@@ -47,6 +48,9 @@ struct TcParams {
 using namespace tc;
 
 // dynamic smem layout (1024 B aligned): [stage][A hi 16K | (A lo 16K) | B hi BN*128 | (B lo BN*128)] ... barriers ... tmem ptr
+// PERSISTENT: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest so neighbouring CTAs share the A tile in
+// L2); the smem ring runs continuously across tiles and the accumulator is double-buffered in TMEM (2 x BN columns), so the
+// epilogue of tile i (TMEM -> registers -> global, BRN statistics) overlaps the main loop of tile i+1.
 template <bool SPLIT3>
 __global__ void __launch_bounds__(SPLIT3 ? 192 + SPLIT_THREADS : 192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -58,16 +62,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* split_bar = empty_bar + p.stages;       // A tile split done (SPLIT3)
-  uint64_t* accum_bar = split_bar + p.stages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = split_bar + p.stages;        // [2] accumulator stage complete (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;               // [2] accumulator stage drained (epilogue -> MMA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
+  const int total_tiles = p.tiles_m * p.tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], SPLIT_THREADS / 32); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -82,176 +87,194 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int pix0 = tile_m * TC_BM;
-      const int img = pix0 / (p.H * p.W);
-      const int y0 = (pix0 - img * p.H * p.W) / p.W;
       const uint32_t tx = (uint32_t)(A_TILE_BYTES + (SPLIT3 ? 2 : 1) * b_bytes);   // A fp32 (split in smem); B hi (+ lo, pre-split)
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = kb / p.kblocks_per_tap;
-        const int c0 = (kb - tap * p.kblocks_per_tap) * TC_BK;
-        const int dy = tap / p.ksz - p.pad, dx = tap % p.ksz - p.pad;
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx);
-        tma_load_4d(&map_a, &full_bar[s], st, c0, dx, y0 + dy, img);
-        uint8_t* bdst = st + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
-        const int wtap = p.flip_taps ? p.ksz * p.ksz - 1 - tap : tap;
-        tma_load_3d(&map_w, &full_bar[s], bdst, c0, n0, wtap);
-        if (SPLIT3) tma_load_3d(&map_wlo, &full_bar[s], bdst + b_bytes, c0, n0, wtap);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
+        const int pix0 = tile_m * TC_BM;
+        const int img = pix0 / (p.H * p.W);
+        const int y0 = (pix0 - img * p.H * p.W) / p.W;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = kb / p.kblocks_per_tap;
+          const int c0 = (kb - tap * p.kblocks_per_tap) * TC_BK;
+          const int dy = tap / p.ksz - p.pad, dx = tap % p.ksz - p.pad;
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx);
+          tma_load_4d(&map_a, &full_bar[s], st, c0, dx, y0 + dy, img);
+          uint8_t* bdst = st + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
+          const int wtap = p.flip_taps ? p.ksz * p.ksz - 1 - tap : tap;
+          tma_load_3d(&map_w, &full_bar[s], bdst, c0, n0, wtap);
+          if (SPLIT3) tma_load_3d(&map_wlo, &full_bar[s], bdst + b_bytes, c0, n0, wtap);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
-        if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);            // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t ad = make_desc(a_addr + k * 32), bd = make_desc(b_addr + k * 32);
-          if (SPLIT3) {
-            const uint64_t ald = make_desc(a_addr + A_TILE_BYTES + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
-            tc_mma_tf32(tmem_base, ad, bld, idesc, (kb | k) != 0);      // hi * lo
-            tc_mma_tf32(tmem_base, ald, bd, idesc, 1);                  // lo * hi
-            tc_mma_tf32(tmem_base, ad, bd, idesc, 1);                   // hi * hi
-          } else {
-            tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t ad = make_desc(a_addr + k * 32), bd = make_desc(b_addr + k * 32);
+            if (SPLIT3) {
+              const uint64_t ald = make_desc(a_addr + A_TILE_BYTES + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
+              tc_mma_tf32(tmem_d, ad, bld, idesc, (kb | k) != 0);      // hi * lo
+              tc_mma_tf32(tmem_d, ald, bd, idesc, 1);                  // lo * hi
+              tc_mma_tf32(tmem_d, ad, bd, idesc, 1);                   // hi * hi
+            } else {
+              tc_mma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0);
+            }
           }
+          tc_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
         }
-        tc_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+        tc_commit(&acc_full[as]);              // accumulator complete -> epilogue
       }
-      tc_commit(accum_bar);                  // accumulator complete -> epilogue
     }
   } else if (warp < 6) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait_sleep(accum_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                              // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int m = tile_m * TC_BM + row;
-    const bool mvalid = m < p.M;
-    float* yr = p.y + (size_t)m * p.y_cs;
-    const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
-    const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
-                        (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     __shared__ float s_sum[4][256], s_sq[4][256];
     __shared__ int s_last;
-    for (int cb = 0; cb < p.BN; cb += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-      if (p.stats) {
-        // column sums over this warp's 32 rows by recursive halving: 31 shuffles, lane l ends with column cb+l
-        float a[32], b2[32];
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int et = q * 32 + lane;                        // 0..127 (warps 2..5 -> q = 2,3,0,1)
+    const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                        (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
+      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait_sleep(&acc_full[as], aph);
+      tc_fence_after();
+      const int m = tile_m * TC_BM + row;
+      const bool mvalid = m < p.M;
+      float* yr = p.y + (size_t)m * p.y_cs;
+      const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
+      for (int cb = 0; cb < p.BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.BN + (uint32_t)cb, v);
+        if (p.stats) {
+          // column sums over this warp's 32 rows by recursive halving: 31 shuffles, lane l ends with column cb+l
+          float a[32], b2[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(v[i]); b2[i] = a[i] * a[i]; }   // rows past M are exact zeros
+          for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(v[i]); b2[i] = a[i] * a[i]; }   // rows past M are exact zeros
 #pragma unroll
-        for (int sft = 16; sft >= 1; sft >>= 1) {
-          const bool up = (lane & sft) != 0;
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
 #pragma unroll
-          for (int j = 0; j < sft; ++j) {
-            const float sa = up ? a[j] : a[j + sft], ka = up ? a[j + sft] : a[j];
-            const float sb = up ? b2[j] : b2[j + sft], kb2 = up ? b2[j + sft] : b2[j];
-            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, sft);
-            b2[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, sft);
+            for (int j = 0; j < sft; ++j) {
+              const float sa = up ? a[j] : a[j + sft], ka = up ? a[j + sft] : a[j];
+              const float sb = up ? b2[j] : b2[j + sft], kb2 = up ? b2[j + sft] : b2[j];
+              a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, sft);
+              b2[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, sft);
+            }
           }
+          s_sum[q][cb + lane] = a[0]; s_sq[q][cb + lane] = b2[0];
         }
-        s_sum[q][cb + lane] = a[0]; s_sq[q][cb + lane] = b2[0];
-      }
-      if (!mvalid) continue;
+        if (!mvalid) continue;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int n = n0 + cb + g * 4;
-        if (n >= p.Cout) break;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int nn = n + e;
-          float x = __uint_as_float(v[g * 4 + e]);
-          if (nn < p.Cout) {
-            if (p.scale) x = x * __ldg(p.scale + nn);
-            if (p.shift) x = x + __ldg(p.shift + nn);
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.dropout) x = dr_hash_keep(p.drop_seed, p.drop_tag, (uint64_t)m * p.Cout + nn) ? x * 2.0f : 0.f;
-          }
-          o[e] = x;
-        }
-        if (vec_ok && n + 3 < p.Cout) {
-          if (rr) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rr + n);
-            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-          }
-          if (p.accumulate) {
-            const float4 y4 = *reinterpret_cast<const float4*>(yr + n);
-            o[0] += y4.x; o[1] += y4.y; o[2] += y4.z; o[3] += y4.w;
-          }
-          *reinterpret_cast<float4*>(yr + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
+        for (int g = 0; g < 8; ++g) {
+          const int n = n0 + cb + g * 4;
+          if (n >= p.Cout) break;
+          float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int nn = n + e;
+            float x = __uint_as_float(v[g * 4 + e]);
             if (nn < p.Cout) {
-              float x = o[e];
-              if (rr) x += rr[nn];
-              if (p.accumulate) x += yr[nn];
-              yr[nn] = x;
+              if (p.scale) x = x * __ldg(p.scale + nn);
+              if (p.shift) x = x + __ldg(p.shift + nn);
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (p.dropout) x = dr_hash_keep(p.drop_seed, p.drop_tag, (uint64_t)m * p.Cout + nn) ? x * 2.0f : 0.f;
+            }
+            o[e] = x;
+          }
+          if (vec_ok && n + 3 < p.Cout) {
+            if (rr) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rr + n);
+              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
+            if (p.accumulate) {
+              const float4 y4 = *reinterpret_cast<const float4*>(yr + n);
+              o[0] += y4.x; o[1] += y4.y; o[2] += y4.z; o[3] += y4.w;
+            }
+            *reinterpret_cast<float4*>(yr + n) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int nn = n + e;
+              if (nn < p.Cout) {
+                float x = o[e];
+                if (rr) x += rr[nn];
+                if (p.accumulate) x += yr[nn];
+                yr[nn] = x;
+              }
             }
           }
         }
       }
-    }
-    if (p.stats) {
-      const int et = q * 32 + lane;                                     // 0..127 (warps 2..5 -> q = 2,3,0,1)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int col = et; col < p.BN; col += 128) {
-        const int n = n0 + col;
-        if (n < p.Cout) {
-          atomicAdd(p.stats + n, (double)((s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col])));
-          atomicAdd(p.stats + p.Cout + n, (double)((s_sq[0][col] + s_sq[1][col]) + (s_sq[2][col] + s_sq[3][col])));
+      // all of this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld32): hand the stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < p.BN; col += 128) {
+          const int n = n0 + col;
+          if (n < p.Cout) {
+            atomicAdd(p.stats + n, (double)((s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col])));
+            atomicAdd(p.stats + p.Cout + n, (double)((s_sq[0][col] + s_sq[1][col]) + (s_sq[2][col] + s_sq[3][col])));
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) s_last = (atomicAdd(p.stats_counter, 1u) == (unsigned)total_tiles - 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last) {                                                     // last TILE of the layer: BRN finalize
+          __threadfence();
+          brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
         }
       }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) s_last = (atomicAdd(p.stats_counter, 1u) == gridDim.x * gridDim.y - 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (s_last) {                                                     // last CTA: BRN finalize for the whole layer
-        __threadfence();
-        brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
-      }
     }
-    tc_fence_before();
   } else if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
     const int t = threadIdx.x - 192;                      // 0..SPLIT_THREADS-1
-    const int na4 = A_TILE_BYTES / 16, nb4 = 0;          // weights arrive pre-split (hi, lo) by TMA; only the A tile is split here
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
-      mbar_wait(&full_bar[s], ph);
-      float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-      float4* a_lo = a_hi + na4;
-      float4* b_hi = a_lo + na4;
-      float4* b_lo = b_hi + b_bytes / 16;
-      for (int idx = t; idx < na4 + nb4; idx += SPLIT_THREADS) {   // elementwise: the swizzled layout is irrelevant
-        float4* hp = idx < na4 ? a_hi + idx : b_hi + (idx - na4);
-        float4* lp = idx < na4 ? a_lo + idx : b_lo + (idx - na4);
-        const float4 a = *hp;
-        float4 h, l;
-        h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
-        h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
-        h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
-        h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
-        *hp = h; *lp = l;
+    const int na4 = A_TILE_BYTES / 16;                    // weights arrive pre-split (hi, lo) by TMA; only the A tile is split here
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+        float4* a_lo = a_hi + na4;
+        for (int idx = t; idx < na4; idx += SPLIT_THREADS) {   // elementwise: the swizzled layout is irrelevant
+          const float4 a = a_hi[idx];
+          float4 h, l;
+          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
+          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
+          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
+          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
+          a_hi[idx] = h; a_lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);                       // one arrival per splitter warp
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&split_bar[s]);                       // one arrival per splitter warp
     }
   }
 
@@ -262,7 +285,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
 }  // namespace
 
 // Weight operands for the tensor-core path are K-major copies [tap][cout][cin] prepared by the engine (p.w points at
@@ -292,8 +314,9 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   if (split3 && BN > 128) BN = 128;                        // 3 stages of [A hi|lo, B hi|lo] fit; 2 stages at BN=256 measured slower
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
-  int cols = 32; while (cols < BN) cols <<= 1;
+  int cols = 32; while (cols < 2 * BN) cols <<= 1;         // two accumulator stages
   t.tmem_cols = cols;
+  t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;
   const int stage_bytes = (split3 ? 2 : 1) * (A_TILE_BYTES + BN * TC_BK * 4);
   int stages = (208 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
@@ -305,7 +328,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   t.accumulate = p.accumulate; t.dropout = p.dropout; t.drop_seed = p.drop_seed; t.drop_tag = p.drop_tag;
   t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
   t.bn_update_state = p.bn_update_state;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (4 * stages + 2) * 8 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
 
   // activation map: dims (C, W, H, B)
   CUtensorMap ma, mw, mwlo;
@@ -324,7 +347,10 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   mwlo = mw;
   if (split3) { if (!encode_map(&mwlo, p.w_kmajor_lo, 3, wd, ws, wb)) return 0; }
 
-  dim3 grid((t.M + TC_BM - 1) / TC_BM, (p.Cout + BN - 1) / BN);
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+  const int total_tiles = t.tiles_m * t.tiles_n;
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (split3) {
     if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[1] = true; }
     conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);

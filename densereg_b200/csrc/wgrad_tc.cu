@@ -197,7 +197,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   t.cin_tiles = (p.Cin + 127) / 128;
   const int cout_tiles = (p.Cout + BN - 1) / BN;
   const int tiles = t.cin_tiles * p.k * p.k * cout_tiles;
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  int splits = (2 * 148) / tiles;                           // floor: keep the CTA count just under 2 full waves of 148 SMs
   if (splits > t.total_kb / 8) splits = t.total_kb / 8;
   if (splits < 1) splits = 1;
   t.kb_per_split = (t.total_kb + splits - 1) / splits;
