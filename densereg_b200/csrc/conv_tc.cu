@@ -18,6 +18,7 @@
 // Warp roles (192 / 320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
 //   (TMEM lane quarter = warp_idx % 4), warps 6-9 operand splitter (3xTF32 only).  mbarrier full/empty ring.
 #include "tc_common.cuh"
+#include <stdlib.h>
 #include "brn.cuh"
 
 namespace {
@@ -312,6 +313,8 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   int BN = (p.Cout + 15) / 16 * 16;
   if (BN > 256) BN = 256;
   if (split3 && BN > 128) BN = 128;                        // 3 stages of [A hi|lo, B hi|lo] fit; 2 stages at BN=256 measured slower
+  { static int bn_cap = -1; if (bn_cap < 0) { const char* e = getenv("DENSEREG_TC_BN"); bn_cap = e ? atoi(e) : 0; }   // tuning knob
+    if (bn_cap >= 16 && BN > bn_cap) BN = bn_cap / 16 * 16; }
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
   int cols = 32; while (cols < 2 * BN) cols <<= 1;         // two accumulator stages

@@ -22,6 +22,7 @@
 
 #define VOTE_K 5
 #define VOTE_MAX_THREADS 256
+#define VOTE_U 8
 
 struct VoteParams {
   int B, H, W, J, G;
@@ -44,6 +45,12 @@ DR_DEVINL void top5_insert(float (&s)[VOTE_K], int (&ix)[VOTE_K], float r, int p
       }
     }
   }
+}
+
+DR_DEVINL float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 
 DR_DEVINL int f2i_trunc_sat(float v) {
@@ -74,18 +81,19 @@ vote_kernel(VoteParams a) {
     const float* hm3 = a.hm3 + (size_t)b * P * a.hm3_cs + j;
     const float* dm = a.dm + (size_t)b * P;
     int p = g;
-    // 4 pixels per trip: issue all loads first (memory-level parallelism), then insert in index order
-    for (; p + 3 * G < P; p += 4 * G) {
-      float d[4], h[4], h3[4];
+    // VOTE_U pixels per trip: issue all loads first (memory-level parallelism: ~3*VOTE_U 4-byte loads in flight per thread,
+    // streaming / no L1 allocation), then insert in index order
+    for (; p + (VOTE_U - 1) * G < P; p += VOTE_U * G) {
+      float d[VOTE_U], h[VOTE_U], h3[VOTE_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VOTE_U; ++u) {
         int q = p + u * G;
-        d[u] = __ldg(dm + q);
-        h[u] = __ldg(hm + (size_t)q * a.hm_cs);
-        h3[u] = __ldg(hm3 + (size_t)q * a.hm3_cs);
+        d[u] = ld_stream(dm + q);
+        h[u] = ld_stream(hm + (size_t)q * a.hm_cs);
+        h3[u] = ld_stream(hm3 + (size_t)q * a.hm3_cs);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VOTE_U; ++u) {
         float r = (h[u] + 1.0f) * h3[u];                 // refined_hms = (hms+1)*hm3s          :764
         r = r * (d[u] < -0.99f ? 0.0f : 1.0f);           // * dms_mask                          :767-768
         top5_insert(sc, ix, r, p + u * G);
