@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--batch_size", type=int, default=40)
     ap.add_argument("--sub_batch", type=int, default=5)
     ap.add_argument("--precision", type=str, default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
-    ap.add_argument("--cpu_batch", type=int, default=8)
+    ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -97,6 +97,10 @@ int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const flo
 // backward reductions: g = dy*(z>0); sums[0:C]=sum g, sums[C:2C]=sum g*xhat   (z = raw*a+b, xhat=(raw-mean)*inv_std)
 int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st);
+// fused cooperative version of the two kernels below (returns 0 if not applicable); counter must be zero on entry
+int launch_brn_bwd_fused(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs, const float* aff, const float* bstat,
+                         const float* beta_gamma, int relu, double* sums, unsigned int* counter, float* draw, int draw_cs, float* gparam,
+                         cudaStream_t st);
 // draw = gamma*r*inv_std*(g - sum_g/N - xhat*sum_gx/N); also dbeta,dgamma accumulated into gparam
 int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                          const float* aff, const float* bstat, const float* beta_gamma, int relu,

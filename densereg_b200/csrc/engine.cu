@@ -68,7 +68,7 @@ struct dr_handle {
   float *wk = nullptr, *wa = nullptr, *wk_hi = nullptr, *wk_lo = nullptr, *wa_hi = nullptr, *wa_lo = nullptr;
   size_t n_wk = 0, n_wa = 0;
   double *sums = nullptr, *sums_bw = nullptr, *loss_acc = nullptr;
-  unsigned int* counters = nullptr;      // one per layer: last-block-done counters of the fused stats+finalize kernel
+  unsigned int* counters = nullptr; unsigned int* counters_bw = nullptr;      // one per layer: last-block-done counters of the fused stats+finalize kernel
   int32_t* clamp_dev = nullptr;
   LayerDev* ltab = nullptr;
   int cap_B = 0; bool cap_train = false;
@@ -524,6 +524,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   int nl = 0;
   const int OUT = h->cfg.out_hw, J = h->cfg.num_jnt, S = h->cfg.num_stack;
   CUDA_TRY(h, cudaMemsetAsync(h->sums_bw, 0, h->n_sums * sizeof(double), st));
+  CUDA_TRY(h, cudaMemsetAsync(h->counters_bw, 0, h->layers.size() * sizeof(unsigned int), st));
   CUDA_TRY(h, cudaMemsetAsync(h->loss_acc, 0, 4 * sizeof(double), st));
   // loss + dL/d(outputs)
   LossArgs la; memset(&la, 0, sizeof(la));
@@ -553,9 +554,14 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         if (L.brn) {
           View rv = X.whole(o.raw);
           double* sums = h->sums_bw + L.sum_off;
-          nl += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
-          nl += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
-                                     h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
+          int nf = launch_brn_bwd_fused(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
+                                        h->params + L.p_off, L.relu, sums, h->counters_bw + o.layer, dz, dz_cs, h->grads + L.p_off, st);
+          if (nf == 0) {
+            nf += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
+            nf += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
+                                       h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
+          }
+          nl += nf;
         } else {
           nl += launch_bias_bwd(np, L.cout, dy, dy_cs, X.ptr(o.out), X.cs(o.out), L.relu, o.dropout_tag >= 0, dz, dz_cs, h->grads + L.p_off, st);
         }
@@ -624,6 +630,7 @@ int init_device(dr_handle* h) {
   CUDA_TRY(h, cudaMalloc(&h->sums_bw, h->n_sums * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->loss_acc, 4 * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->counters, h->layers.size() * sizeof(unsigned int)));
+  CUDA_TRY(h, cudaMalloc(&h->counters_bw, h->layers.size() * sizeof(unsigned int)));
   CUDA_TRY(h, cudaMalloc(&h->clamp_dev, sizeof(int32_t)));
   CUDA_TRY(h, cudaMemcpy(h->ltab, tab.data(), tab.size() * sizeof(LayerDev), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->wdmask, wdm.data(), wdm.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -659,7 +666,7 @@ int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
   cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
-  cudaFree(h->clamp_dev); cudaFree(h->ltab); cudaFree(h->counters);
+  cudaFree(h->clamp_dev); cudaFree(h->ltab); cudaFree(h->counters); cudaFree(h->counters_bw);
   delete h;
   return DR_OK;
 }
