@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -77,6 +78,12 @@ struct dr_handle {
   std::string err;
   int precision = 0;
   int64_t tc_launches = 0;
+  // backward: filter gradients run on a side stream (they only feed the optimiser) so that they fill the SMs the small
+  // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
+  static const int kScratchSlots = 3;
+  cudaStream_t wgrad_stream = nullptr;
+  cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr}, ev_wdone[3] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
+  bool side_stream = true;
 };
 
 namespace {
@@ -423,8 +430,17 @@ int ensure_workspace(dr_handle* h, int B, bool train) {
     CUDA_TRY(h, cudaMemset(h->gact, 0, bytes));
     bytes = h->raw_per_crop * cap * sizeof(float);
     CUDA_TRY(h, cudaMalloc(&h->rawa, bytes)); h->ws_bytes += bytes;
-    bytes = h->scratch_per_crop * cap * sizeof(float);
+    bytes = h->scratch_per_crop * cap * sizeof(float) * dr_handle::kScratchSlots;
     CUDA_TRY(h, cudaMalloc(&h->scratch, bytes)); h->ws_bytes += bytes;
+    { const char* env = getenv("DENSEREG_SIDE_STREAM"); h->side_stream = !(env && env[0] == '0'); }
+    if (h->side_stream) {
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < dr_handle::kScratchSlots; ++i) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wdone[i], cudaEventDisableTiming));
+      }
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     h->cap_train = true;
   }
   h->cap_B = cap;
@@ -539,6 +555,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   nl += launch_wd(h->n_params, h->params, h->wdmask, h->grads, h->loss_acc + 3, st);
   if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
 
+  int conv_idx = 0;
   for (int oi = (int)h->ops.size() - 1; oi >= 0; --oi) {
     const Op& o = h->ops[oi];
     switch (o.kind) {
@@ -550,7 +567,9 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           nl += apply_fills(h, X, o.gw_res, st);
           nl += launch_copy_view(np, o.res.C, dy, dy_cs, X.gptr(o.res), X.cs(o.res), o.gw_res.acc, nullptr, st);
         }
-        float* dz = h->scratch; const int dz_cs = (L.cout + 3) / 4 * 4;
+        const int slot = conv_idx % dr_handle::kScratchSlots; ++conv_idx;
+        float* dz = h->scratch + (size_t)slot * h->scratch_per_crop * h->cap_B; const int dz_cs = (L.cout + 3) / 4 * 4;
+        if (h->side_stream) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_wdone[slot], 0));   // the wgrad that last read this slot is done
         if (L.brn) {
           View rv = X.whole(o.raw);
           double* sums = h->sums_bw + L.sum_off;
@@ -570,7 +589,14 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin; wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout;
         wp.k = L.k; wp.stride = L.stride; wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         wp.dw = h->grads + L.w_off;
-        nl += run_wgrad(h, wp, h->precision, st);
+        if (h->side_stream) {
+          CUDA_TRY(h, cudaEventRecord(h->ev_ready[slot], st));
+          CUDA_TRY(h, cudaStreamWaitEvent(h->wgrad_stream, h->ev_ready[slot], 0));
+          nl += run_wgrad(h, wp, h->precision, h->wgrad_stream);
+          CUDA_TRY(h, cudaEventRecord(h->ev_wdone[slot], h->wgrad_stream));
+        } else {
+          nl += run_wgrad(h, wp, h->precision, st);
+        }
         if (o.need_dgrad) {
           nl += apply_fills(h, X, o.gw_in, st);
           ConvProblem p; memset(&p, 0, sizeof(p));
@@ -604,6 +630,10 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
                                X.ptr(X.whole(h->buf_tiny)), st);
         break;
     }
+  }
+  if (h->side_stream) {          // the optimiser step / next micro-batch on `st` must see every filter gradient
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->wgrad_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   h->launches += nl;
   CUDA_TRY(h, cudaGetLastError());
@@ -664,6 +694,9 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
 
 int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
+  if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
+  for (int i = 0; i < 3; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_wdone[i]) cudaEventDestroy(h->ev_wdone[i]); }
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
   cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
   cudaFree(h->clamp_dev); cudaFree(h->ltab); cudaFree(h->counters); cudaFree(h->counters_bw);
