@@ -84,70 +84,117 @@ def cpu_reference_step(net, U, params, state, m, v, batch, step, J):
     return L["total"]
 
 
-class CpuReference:
-    """CPU restatement of the reference graph (oracle port; TF 1.3 cannot run here), time-boxed.
+def usable_cpus():
+    """Hardware threads this process may really use: affinity mask capped by the cgroup CPU quota (a shared GPU host reports
+    128 CPUs but the container may be throttled to a fraction; oversubscribing a quota makes PyTorch-CPU 10-100x slower)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, p = open(path).read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(int(q) / int(p))))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            n = min(n, max(1, q // p))
+    except Exception:
+        pass
+    return max(1, n)
 
-    PyTorch-CPU with every hardware thread of a 128-thread shared host can be SLOWER than with 32 threads for these
-    small 32x32 maps, so both thread counts are calibrated on a 1-crop step and the faster one is used and reported
-    (`cores` = threads actually used).  The per-step sample (crops per micro-batch) is sized from the calibration so
-    that one step takes about `target_s` seconds."""
 
-    def __init__(self, S=2, F=128, J=16, target_s=4.0, max_batch=8):
+def _cpu_worker(conn, steps, warmup, target_s, max_batch):
+    """Child process: CPU restatement of the reference graph (oracle port).  Reports after every timed step so that the
+    parent can enforce a wall-clock box and still use what was measured."""
+    try:
         import torch
         from oracle import um_v1_torch as U
         from densereg_b200 import synth
-        self.torch, self.U, self.synth, self.J = torch, U, synth, J
-        self.net = U.Net(S, F, J)
-        self.p, self.s = self.net.init_params(0), self.net.init_state()
-        self.m, self.v = torch.zeros_like(self.p), torch.zeros_like(self.p)
-        self.step_no = 0
-        cores = os.cpu_count() or 1
+        J = 16
+        threads = usable_cpus()
+        torch.set_num_threads(threads)
+        net = U.Net(2, 128, J)
+        p, s = net.init_params(0), net.init_state()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        state = {"n": 0}
+
+        def step(batch):
+            state["n"] += 1
+            return cpu_reference_step(net, U, p, s, m, v, batch, state["n"], J)
+
         one = synth.make_batch(1, J, seed=0)
-        best = None
-        for threads in sorted({min(cores, 32), cores}):
-            torch.set_num_threads(threads)
-            self._step(one)                                   # primitive creation / first touch
-            t0 = time.perf_counter(); self._step(one); dt = time.perf_counter() - t0
-            if best is None or dt < best[1]:
-                best = (threads, dt)
-        self.threads, self.t1 = best
-        torch.set_num_threads(self.threads)
-        self.batch_size = int(max(1, min(max_batch, round(target_s / max(self.t1, 1e-3)))))
-        self.batch = synth.make_batch(self.batch_size, J, seed=1)
-        self.sample = ("fwd+bwd+Adam on one micro-batch of %d crop(s) per step (instead of 5x40); %d of %d host threads "
-                       "(faster of {32, all} on a 1-crop calibration step: %.2f s)" % (self.batch_size, self.threads, cores, self.t1))
-
-    def _step(self, batch):
-        self.step_no += 1
-        return cpu_reference_step(self.net, self.U, self.p, self.s, self.m, self.v, batch, self.step_no, self.J)
-
-    def run(self, steps, warmup, budget_s=None):
-        """-> (crops/s, steps actually timed).  With a budget the timed loop stops early (>= 1 step)."""
+        step(one)                                             # primitive creation / first touch
+        t0 = time.perf_counter(); step(one); t1 = time.perf_counter() - t0
+        bsz = int(max(1, min(max_batch, round(target_s / max(t1, 1e-3)))))
+        sample = ("fwd+bwd+Adam on one micro-batch of %d crop(s) per step (instead of 5x40), %d threads "
+                  "(usable CPUs of %d reported; 1-crop calibration step %.2f s)" % (bsz, threads, os.cpu_count() or 0, t1))
+        conn.send({"phase": "calib", "value": 1.0 / t1, "steps": 1, "dt": t1, "threads": threads, "sample": sample, "batch": 1})
+        batch = synth.make_batch(bsz, J, seed=1)
         for _ in range(warmup):
-            self._step(self.batch)
-        t0 = time.perf_counter(); n = 0
-        for _ in range(steps):
-            self._step(self.batch); n += 1
-            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            step(batch)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(batch)
+            dt = time.perf_counter() - t0
+            conn.send({"phase": "timed", "value": bsz * (i + 1) / dt, "steps": i + 1, "dt": dt, "threads": threads, "sample": sample,
+                       "batch": bsz})
+        conn.send({"phase": "done"})
+    except Exception as e:                                     # pragma: no cover
+        conn.send({"phase": "error", "error": repr(e)})
+
+
+def run_cpu_reference(steps, warmup, wall_s, target_s=3.0, max_batch=8):
+    """-> dict(value, steps, dt, threads, sample, complete) or None.  Never takes longer than wall_s seconds."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe(duplex=False)
+    proc = ctx.Process(target=_cpu_worker, args=(child, steps, warmup, target_s, max_batch), daemon=True)
+    proc.start()
+    deadline = time.time() + wall_s
+    last, complete = None, False
+    while time.time() < deadline:
+        if parent.poll(0.5):
+            msg = parent.recv()
+            if msg.get("phase") == "done":
+                complete = True
                 break
-        dt = time.perf_counter() - t0
-        return self.batch_size * n / dt, n, dt
+            if msg.get("phase") == "error":
+                last = last or {"value": None, "steps": 0, "dt": 0.0, "threads": usable_cpus(), "sample": "oracle failed: " + msg["error"]}
+                break
+            last = msg
+        elif not proc.is_alive():
+            break
+    if proc.is_alive():
+        proc.kill()                                            # exact PID of the child we started
+    proc.join(5)
+    if last is not None:
+        last["complete"] = complete
+        if not complete:
+            last["sample"] += " [stopped by the %d s wall-clock box after %d timed step(s)]" % (int(wall_s), last.get("steps", 0))
+    return last
 
 
 def run_reference(args):
-    """--impl reference: each step is a bounded sample of the workload (one micro-batch sized by calibration)."""
+    """--impl reference: each step is a bounded sample of the workload (one micro-batch sized by calibration); the whole run is
+    boxed to a few minutes."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    ref = CpuReference(target_s=3.0)
-    val, n, dt = ref.run(args.steps, args.warmup)
+    r = run_cpu_reference(args.steps, args.warmup, wall_s=float(os.environ.get("DENSEREG_REF_WALL_S", "240")))
+    if r is None or r.get("value") is None:
+        r = {"value": 0.0, "steps": 0, "dt": 0.0, "threads": usable_cpus(), "sample": "CPU restatement produced no step inside the time box"}
+    val = r["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": (r["dt"] / max(r["steps"], 1)) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "ICVL J=16 2-stack fea=128 training step, CPU restatement of the reference TF graph (PyTorch-CPU fp32)",
-                   "sample": ref.sample},
-        "cpu_baseline": {"value": val, "unit": "crops/s", "cores": ref.threads, "kind": "port", "sample": ref.sample},
+                   "sample": r["sample"], "timed_steps": r["steps"]},
+        "cpu_baseline": {"value": val, "unit": "crops/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -268,10 +315,13 @@ def main():
     if rank == 0:
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
-            ref = CpuReference(target_s=4.0)
-            cval, n, dt = ref.run(steps=4, warmup=0, budget_s=20.0)       # time-boxed: ~10-30 s of CPU work
-            cpu_baseline = {"value": cval, "unit": "crops/s", "cores": ref.threads, "kind": "port",
-                            "sample": "%d timed step(s): %s" % (n, ref.sample)}
+            r = run_cpu_reference(steps=4, warmup=0, wall_s=float(os.environ.get("DENSEREG_CPU_WALL_S", "75")), target_s=4.0)
+            if r is not None and r.get("value") is not None:
+                cpu_baseline = {"value": r["value"], "unit": "crops/s", "cores": r["threads"], "kind": "port",
+                                "sample": "%d timed step(s): %s" % (r["steps"], r["sample"])}
+            else:
+                cpu_baseline = {"value": None, "unit": "crops/s", "cores": usable_cpus(), "kind": "port",
+                                "sample": "CPU restatement did not finish a step inside the 75 s box"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
