@@ -24,6 +24,10 @@ sys.path.insert(0, ROOT)
 # SURVEY.md 8d / BASELINE.md section 2: algorithmic conv FLOPs per crop, training = 3 x forward
 TRAIN_GFLOP_PER_CROP = {16: 29.37, 14: 29.19, 21: 29.82}
 METRIC = "depth-crops/sec (128x128, 2-stack fea=128) training step"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (conv on s0/um_comb/c2, B=40), from the
+# `ncu --set full` captures summarised in profiles/r1_tensor_core_path.md (algorithmic: 42 MB in + 42 MB out + 2.4 MB weights;
+# the output is still L2-resident when the capture ends)
+NCU_TRAFFIC_BYTES = {"tf32x3": 48.5e6, "tf32": 47.4e6, "fp32": 51.0e6}
 
 
 def measured_peaks():
@@ -306,7 +310,7 @@ def main():
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     step_tflops = value / world * TRAIN_GFLOP_PER_CROP[J] / 1e3
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                "frac": achieved / peaks["bf16_burst"], "traffic": NCU_TRAFFIC_BYTES.get(args.precision),
                 "kernel": "conv implicit-GEMM (%s path) on s0/um_comb/c2 3x3 256->256, B=%d" % (args.precision, B),
                 "kernel_ms": k_ms, "peak_source": peaks["src"] + " dense bf16 cuBLAS burst (tf32 kind nominally half)",
                 "whole_step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"], "frac": step_tflops / peaks["bf16_sustained"],
