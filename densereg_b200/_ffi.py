@@ -45,6 +45,9 @@ SIGNATURES = {
     "dr_loss_backward": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _F, C.c_uint64, C.c_int, _P]),
     "dr_zero_grads": (C.c_int, [_P, _P]),
     "dr_optimizer_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int64, _P]),
+    "dr_crop_from_xyz_pose": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float,
+                                        C.c_int, _F, _F, _F, _P]),
+    "dr_crop_from_bbx": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, C.POINTER(C.c_float), C.c_int, _F, _F, _F, _P]),
     "dr_debug_conv": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, C.c_int, _P]),
     "dr_debug_conv_bwd": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, C.c_int, _P]),
     "dr_debug_get_output": (C.c_int, [_P, C.c_int, C.c_int, _F, C.c_int, _P]),

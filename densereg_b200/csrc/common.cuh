@@ -125,3 +125,8 @@ int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float in
 int launch_transpose_weights(int k, int cin, int cout, const float* w, float* wt, cudaStream_t st);
 int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st);
 int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, float* dst, cudaStream_t st);
+
+// ---- crop + centre-of-mass front-end (crop.cu) ---------------------------------------------------
+size_t crop_scratch_bytes(int B);
+int launch_crop(int B, int in_h, int in_w, const float* frames, const float* poses, int J, const float* bbx, const float cfg_host[6],
+                int out_hw, float pad, int icvl, void* scratch, float* dm_out, float* cfg_out, float* com_out, cudaStream_t st);

@@ -71,6 +71,7 @@ struct dr_handle {
   double *sums = nullptr, *sums_bw = nullptr, *loss_acc = nullptr;
   unsigned int* counters = nullptr; unsigned int* counters_bw = nullptr;      // one per layer: last-block-done counters of the fused stats+finalize kernel
   int32_t* clamp_dev = nullptr;
+  void* crop_scratch = nullptr; size_t crop_scratch_cap = 0;
   LayerDev* ltab = nullptr;
   int cap_B = 0; bool cap_train = false;
   size_t ws_bytes = 0;
@@ -699,7 +700,7 @@ int dr_destroy(dr_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
   cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
-  cudaFree(h->clamp_dev); cudaFree(h->ltab); cudaFree(h->counters); cudaFree(h->counters_bw);
+  cudaFree(h->clamp_dev); cudaFree(h->crop_scratch); cudaFree(h->ltab); cudaFree(h->counters); cudaFree(h->counters_bw);
   delete h;
   return DR_OK;
 }
@@ -837,6 +838,33 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
                              lr_t, (float)b1, (float)b2, 1e-8f, (cudaStream_t)stream);
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
+}
+
+static int crop_common(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* poses, int J, const float* bbx,
+                       const float* cfg_host6, int out_hw, float pad, int icvl, float* dm_out, float* cfg_out, float* com_out, void* stream) {
+  if (!h || !frames || !cfg_host6 || !dm_out || !cfg_out || !com_out || B < 1 || in_h < 2 || in_w < 2 || out_hw < 2 || out_hw > 1024)
+    return DR_ERR_ARG;
+  const size_t need = crop_scratch_bytes(B);
+  if (need > h->crop_scratch_cap) {
+    cudaFree(h->crop_scratch); h->crop_scratch = nullptr; h->crop_scratch_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->crop_scratch, need)); h->crop_scratch_cap = need;
+  }
+  h->launches += launch_crop(B, in_h, in_w, frames, poses, J, bbx, cfg_host6, out_hw, pad, icvl, h->crop_scratch, dm_out, cfg_out, com_out,
+                             (cudaStream_t)stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return DR_OK;
+}
+
+int dr_crop_from_xyz_pose(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* poses, int J,
+                          const float* cfg_host6, int out_hw, float pad, int icvl, float* dm_out, float* cfg_out, float* com_out, void* stream) {
+  if (!poses || J < 1) return DR_ERR_ARG;
+  return crop_common(h, B, in_h, in_w, frames, poses, J, nullptr, cfg_host6, out_hw, pad, icvl, dm_out, cfg_out, com_out, stream);
+}
+
+int dr_crop_from_bbx(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* bbx, const float* cfg_host6, int out_hw,
+                     float* dm_out, float* cfg_out, float* com_out, void* stream) {
+  if (!bbx) return DR_ERR_ARG;
+  return crop_common(h, B, in_h, in_w, frames, nullptr, 0, bbx, cfg_host6, out_hw, 0.f, 0, dm_out, cfg_out, com_out, stream);
 }
 
 int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {

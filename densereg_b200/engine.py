@@ -134,6 +134,26 @@ class DenseRegEngine:
         self._check(self.lib.dr_infer(self._h, B, _ptr(dm_mm), _ptr(cfgs), _ptr(coms), _ptr(out), _ptr(top5), self._stream()))
         return out
 
+    def crop_from_xyz_pose(self, frames, poses, cfg, out_hw=128, pad=20.0, icvl=False):
+        """data/preprocess.py crop_from_xyz_pose + center_of_mass on full depth frames (B,in_h,in_w) -> (dms, cfgs, coms)."""
+        B, in_h, in_w = frames.shape
+        kw = dict(dtype=torch.float32, device=self.device)
+        dms = torch.empty(B, out_hw, out_hw, 1, **kw); cfgs = torch.empty(B, 6, **kw); coms = torch.empty(B, 3, **kw)
+        c6 = (C.c_float * 6)(*[float(x) for x in cfg])
+        self._check(self.lib.dr_crop_from_xyz_pose(self._h, B, in_h, in_w, _ptr(frames), _ptr(poses), poses.shape[1] // 3, c6, out_hw,
+                                                   float(pad), int(icvl), _ptr(dms), _ptr(cfgs), _ptr(coms), self._stream()))
+        return dms, cfgs, coms
+
+    def crop_from_bbx(self, frames, bbx, cfg, out_hw=128):
+        """data/preprocess.py crop_from_bbx + center_of_mass (NYU test boxes [top,left,bottom,right,d_th])."""
+        B, in_h, in_w = frames.shape
+        kw = dict(dtype=torch.float32, device=self.device)
+        dms = torch.empty(B, out_hw, out_hw, 1, **kw); cfgs = torch.empty(B, 6, **kw); coms = torch.empty(B, 3, **kw)
+        c6 = (C.c_float * 6)(*[float(x) for x in cfg])
+        self._check(self.lib.dr_crop_from_bbx(self._h, B, in_h, in_w, _ptr(frames), _ptr(bbx), c6, out_hw, _ptr(dms), _ptr(cfgs),
+                                              _ptr(coms), self._stream()))
+        return dms, cfgs, coms
+
     def zero_grads(self):
         self._check(self.lib.dr_zero_grads(self._h, self._stream()))
 

@@ -76,3 +76,34 @@ def make_vote_maps(batch, num_jnt, hw=32, seed=0):
         cfgs[b] = [f, f, cx, cy, 128, 128]
         coms[b] = [(64 - cx) * com_z / f, (64 - cy) * com_z / f, com_z]
     return hm, hm3, um, dmn, cfgs, coms
+
+
+# full-frame camera intrinsics of the three datasets [fx, fy, cx, cy, w, h] (data/icvl.py:12, nyu.py:13, msra.py:13)
+DATASET_CFG = {"icvl": (241.42, 241.42, 160.0, 120.0, 320.0, 240.0),
+               "nyu": (588.235, 587.084, 320.0, 240.0, 640.0, 480.0),
+               "msra": (241.42, 241.42, 160.0, 120.0, 320.0, 240.0)}
+
+
+def make_frames(batch, num_jnt, dataset="icvl", seed=0):
+    """Synthetic FULL depth frames (B,h,w) mm with a hand-like blob, a background wall, joints on the blob (xyz mm in camera
+    coordinates) -- input of the crop + centre-of-mass front-end (data/preprocess.py:10-142)."""
+    rng = np.random.RandomState(seed)
+    fx, fy, cx, cy, w, h = DATASET_CFG[dataset]
+    w, h = int(w), int(h)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    frames = np.zeros((batch, h, w), np.float32)
+    poses = np.zeros((batch, 3 * num_jnt), np.float32)
+    for b in range(batch):
+        z0 = rng.uniform(300.0, 450.0)
+        ex, ey = rng.uniform(0.3 * w, 0.7 * w), rng.uniform(0.3 * h, 0.7 * h)
+        ra, rb = rng.uniform(0.08, 0.16) * w, rng.uniform(0.12, 0.22) * h
+        mask = ((xx - ex) / ra) ** 2 + ((yy - ey) / rb) ** 2 <= 1.0
+        relief = gaussian_filter(rng.randn(h, w).astype(np.float32), 8.0)
+        relief /= (np.abs(relief).max() + 1e-6)
+        dm = np.where(mask, z0 + 40.0 * relief, rng.uniform(700.0, 900.0) if rng.rand() < 0.5 else 0.0).astype(np.float32)
+        ys, xs = np.nonzero(mask)
+        pick = rng.randint(0, len(ys), size=num_jnt)
+        z = dm[ys[pick], xs[pick]] + rng.uniform(-15, 15, size=num_jnt)
+        poses[b] = np.stack([(xs[pick] - cx) * z / fx, (ys[pick] - cy) * z / fy, z], axis=1).reshape(-1)
+        frames[b] = dm
+    return frames, poses, np.array([fx, fy, cx, cy, w, h], np.float32)

@@ -138,6 +138,18 @@ DR_API int dr_zero_grads(dr_handle* h, void* stream);
  * step is the 1-based optimiser step. */
 DR_API int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_t step, void* stream);
 
+/* Depth-frame front-end ("next" row 8f-1): data/preprocess.py:10-79 crop_from_xyz_pose + :131-142 center_of_mass.
+ * frames (B,in_h,in_w) raw depth mm, poses (B,3J) xyz mm (GT or estimated), cfg: 6 floats on the HOST [fx,fy,cx,cy,w,h] of the
+ * full frame (data/icvl.py:12, nyu.py:13, msra.py:13), pad = 20, icvl != 0 selects the fixed 500 mm threshold (:62-63).
+ * Outputs: dm_out (B,out_hw,out_hw,1), cfg_out (B,6) crop intrinsics, com_out (B,3) mm -- exactly the (dms, cfgs, coms) batch
+ * that dr_infer / dr_loss_backward consume. */
+DR_API int dr_crop_from_xyz_pose(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* poses, int J,
+                                 const float* cfg_host6, int out_hw, float pad, int icvl,
+                                 float* dm_out, float* cfg_out, float* com_out, void* stream);
+/* data/preprocess.py:81-129 crop_from_bbx: bbx (B,5) device [top,left,bottom,right,d_th] (data/nyu_bbx.pkl rows). */
+DR_API int dr_crop_from_bbx(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* bbx, const float* cfg_host6,
+                            int out_hw, float* dm_out, float* cfg_out, float* com_out, void* stream);
+
 /* per-conv debug entry used by the parity tests: runs ONE conv of the table on caller data.
  * x (B,H,W,cin) dense -> y (B,Ho,Wo,cout) = conv(x, W[idx]) (no BRN/bias/activation). */
 DR_API int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream);
