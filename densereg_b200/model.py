@@ -81,6 +81,25 @@ def maxJntError(skel1, skel2):       # data/evaluation.py:9-12
     return float(np.max(np.sqrt(np.sum(d ** 2, axis=1))))
 
 
+def error_curve(max_errors):
+    """data/evaluation.py:63-103 plotError: fraction of frames whose MAX joint error is below 10.5/20.5/30.5/40.5 mm and the
+    (threshold, percentage) curve at 0.5, 5.5, ..., 80.5 mm that the reference writes to `<result>_error.txt`."""
+    s = sorted(float(x) for x in max_errors)
+    n = max(len(s), 1)
+    within = {t: sum(1 for v in s if v <= t + 0.5) / n for t in (10, 20, 30, 40)}
+    thresh = [t * 5.0 + 0.5 for t in range(17)]
+    curve = [(t, 100.0 * sum(1 for v in s if v < t) / n) for t in thresh]
+    return within, curve
+
+
+def write_error_curve(max_errors, path):
+    within, curve = error_curve(max_errors)
+    with open(path, "w") as f:
+        for t, p in curve:
+            f.write("%f %f\n" % (t, p))                                                 # evaluation.py:99-101
+    return within
+
+
 def format_result_row(name, xyz_val):
     """model/test_model.py:74-75."""
     res_str = "%s\t%s\n" % (name, "\t".join(format(float(pt), ".4f") for pt in xyz_val))
@@ -221,8 +240,9 @@ def test(model, out_path=None, log=print):
                 if n >= total:
                     break
             step += 1
-    log("finish test: %d frames, mean joint err %.3f mm, mean max-joint err %.3f mm -> %s"
-        % (n, float(np.nanmean(errs)), float(np.nanmean(maxs)), out_path))
+    within = write_error_curve([v for v in maxs if np.isfinite(v)], out_path.replace(".txt", "_error.txt"))   # test_model.py:82
+    log("finish test: %d frames, mean joint err %.3f mm, mean max-joint err %.3f mm, <=10/20/30/40 mm: %s -> %s"
+        % (n, float(np.nanmean(errs)), float(np.nanmean(maxs)), " ".join("%.3f" % within[t] for t in (10, 20, 30, 40)), out_path))
     return float(np.nanmean(errs)), float(np.nanmean(maxs))
 
 

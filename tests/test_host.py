@@ -89,3 +89,30 @@ def test_data_parallel_world2_gloo_equals_accumulation(tmp_path):
     U.adam_step(p, gsum, m, v, step=1, lr=1e-3, accum_steps=2, world=1)
     assert float((got["g"] - gsum).abs().max() / gsum.abs().max()) < 1e-5
     assert float((got["p"] - p).abs().max()) < 1e-6
+
+
+def test_error_curve_matches_reference_definition(tmp_path):
+    from densereg_b200.model import error_curve, write_error_curve
+    errs = [3.0, 10.4, 10.6, 25.0, 39.0, 41.0, 90.0, 0.2]
+    within, curve = error_curve(errs)
+    assert within[10] == 3 / 8 and within[20] == 4 / 8 and within[30] == 5 / 8 and within[40] == 6 / 8      # <= t + 0.5
+    assert curve[0] == (0.5, 100.0 * 1 / 8) and curve[-1] == (80.5, 100.0 * 7 / 8) and len(curve) == 17   # strict <
+    write_error_curve(errs, str(tmp_path / "e.txt"))
+    rows = open(tmp_path / "e.txt").read().strip().split("\n")
+    assert len(rows) == 17 and rows[0].startswith("0.500000 12.5")
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints ONE JSON line with the contract keys (the CPU restatement, time-boxed)."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DENSEREG_REF_WALL_S="60")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=280, env=env, cwd=root)
+    line = [l for l in out.stdout.strip().split("\n") if l.startswith("{")][-1]
+    d = json.loads(line)
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "crops/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
