@@ -48,6 +48,7 @@ SIGNATURES = {
     "dr_crop_from_xyz_pose": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float,
                                         C.c_int, _F, _F, _F, _P]),
     "dr_crop_from_bbx": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, C.POINTER(C.c_float), C.c_int, _F, _F, _F, _P]),
+    "dr_data_aug": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, _F, _F, _F, _F, _F, _F, _P]),
     "dr_debug_conv": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, C.c_int, _P]),
     "dr_debug_conv_bwd": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, C.c_int, _P]),
     "dr_debug_get_output": (C.c_int, [_P, C.c_int, C.c_int, _F, C.c_int, _P]),

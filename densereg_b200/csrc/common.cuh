@@ -130,3 +130,5 @@ int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, floa
 size_t crop_scratch_bytes(int B);
 int launch_crop(int B, int in_h, int in_w, const float* frames, const float* poses, int J, const float* bbx, const float cfg_host[6],
                 int out_hw, float pad, int icvl, void* scratch, float* dm_out, float* cfg_out, float* com_out, cudaStream_t st);
+int launch_data_aug(int B, int hw, int J, const float* dms, const float* poses, const float* cfgs, const float* coms, const float* cossin,
+                    const float* edge_ratio, float* dms_out, float* poses_out, cudaStream_t st);

@@ -131,7 +131,67 @@ __global__ void crop_com_kernel(int B, int out_hw, const double* __restrict__ su
   com[b * 3 + 2] = ave_d;
 }
 
+// ---- data augmentation: data/preprocess.py:234-267 data_aug ------------------------------------------------------
+// rotate (tf.contrib.image.rotate, NEAREST) -> nearest resize by edge_ratio -> centred crop/pad back to (h,w), composed into ONE
+// gather per output pixel; the random draws (cos/sin of the angle, edge ratios) are inputs so the result is reproducible.
+__device__ __forceinline__ int round_half_away(float v) { return (int)(v >= 0.f ? floorf(v + 0.5f) : ceilf(v - 0.5f)); }
+
+__global__ void data_aug_image_kernel(int B, int h, int w, const float* __restrict__ dms, const float* __restrict__ cs /*B,2*/,
+                                      const float* __restrict__ er /*B,2*/, float* __restrict__ out) {
+  const size_t n = (size_t)B * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((size_t)h * w)); const int r = (int)(i - (size_t)b * h * w); const int y = r / w, x = r - y * w;
+    const float cost = cs[b * 2], sint = cs[b * 2 + 1];
+    const int th = (int)((float)h * er[b * 2]), tw = (int)((float)w * er[b * 2 + 1]);       // tf.to_int32(tf.to_float(shape)*ratio)
+    // resize_image_with_crop_or_pad (floor-division offsets)
+    const int wd = w - tw, hd = h - th;
+    auto fdiv2 = [](int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); };                      // python floor division by 2
+    const int ocw = max(fdiv2(-wd), 0), opw = max(fdiv2(wd), 0), och = max(fdiv2(-hd), 0), oph = max(fdiv2(hd), 0);
+    const int yr = y - oph + och, xr = x - opw + ocw;                                         // coordinate in the resized image
+    float v = 0.f;
+    if (y >= oph && x >= opw && yr < th && xr < tw && (y - oph) < (th < h ? th : h) && (x - opw) < (tw < w ? tw : w)) {
+      // ResizeNearestNeighbor, align_corners = false
+      int ys = (int)floorf((float)yr * ((float)h / (float)th)); if (ys > h - 1) ys = h - 1;
+      int xs = (int)floorf((float)xr * ((float)w / (float)tw)); if (xs > w - 1) xs = w - 1;
+      // projective transform of tf.contrib.image.rotate (output -> input), NEAREST
+      const float x_off = ((float)(w - 1) - (cost * (float)(w - 1) - sint * (float)(h - 1))) / 2.0f;
+      const float y_off = ((float)(h - 1) - (sint * (float)(w - 1) + cost * (float)(h - 1))) / 2.0f;
+      const float xi = (cost * (float)xs + (-sint) * (float)ys) + x_off;
+      const float yi = (sint * (float)xs + cost * (float)ys) + y_off;
+      const int rx = round_half_away(xi), ry = round_half_away(yi);
+      if (rx >= 0 && rx < w && ry >= 0 && ry < h) v = dms[((size_t)b * h + ry) * w + rx];
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void data_aug_pose_kernel(int B, int J, const float* __restrict__ poses, const float* __restrict__ cfgs, const float* __restrict__ coms,
+                                     const float* __restrict__ cs, const float* __restrict__ er, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * J) return;
+  const int b = i / J;
+  const float* cfg = cfgs + b * 6; const float* com = coms + b * 3; const float* p = poses + (size_t)i * 3;
+  const float cost = cs[b * 2], sint = cs[b * 2 + 1];
+  const float ucom = (com[0] * cfg[0]) / com[2] + cfg[2], vcom = (com[1] * cfg[1]) / com[2] + cfg[3];   // xyz2uvd_op(com) :241
+  const float u = ((p[0] * cfg[0]) / p[2] + cfg[2]) - ucom, v = ((p[1] * cfg[1]) / p[2] + cfg[3]) - vcom, d = p[2] - com[2];
+  float ur = u * cost + v * sint, vr = u * (-sint) + v * cost;                                           // uvd_pt @ rot_mat :247
+  ur = ur * er[b * 2 + 1] + ucom; vr = vr * er[b * 2] + vcom;                                           // :258-260
+  const float dr = d + com[2];
+  out[(size_t)i * 3 + 0] = ((ur - cfg[2]) * dr) / cfg[0];                                               // uvd2xyz_op :261 (util.py:21)
+  out[(size_t)i * 3 + 1] = ((vr - cfg[3]) * dr) / cfg[1];
+  out[(size_t)i * 3 + 2] = dr;
+}
+
 }  // namespace
+
+int launch_data_aug(int B, int hw, int J, const float* dms, const float* poses, const float* cfgs, const float* coms, const float* cossin,
+                    const float* edge_ratio, float* dms_out, float* poses_out, cudaStream_t st) {
+  const size_t n = (size_t)B * hw * hw;
+  int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  data_aug_image_kernel<<<blocks, 256, 0, st>>>(B, hw, hw, dms, cossin, edge_ratio, dms_out);
+  data_aug_pose_kernel<<<(B * J + 127) / 128, 128, 0, st>>>(B, J, poses, cfgs, coms, cossin, edge_ratio, poses_out);
+  return 2;
+}
 
 int launch_crop(int B, int in_h, int in_w, const float* frames, const float* poses, int J, const float* bbx, const float cfg_host[6],
                 int out_hw, float pad, int icvl, void* scratch /* B*(sizeof(CropParams)+16) bytes */, float* dm_out, float* cfg_out,

@@ -867,6 +867,14 @@ int dr_crop_from_bbx(dr_handle* h, int B, int in_h, int in_w, const float* frame
   return crop_common(h, B, in_h, in_w, frames, nullptr, 0, bbx, cfg_host6, out_hw, 0.f, 0, dm_out, cfg_out, com_out, stream);
 }
 
+int dr_data_aug(dr_handle* h, int B, int hw, int J, const float* dms, const float* poses, const float* cfgs, const float* coms,
+                const float* cossin, const float* edge_ratio, float* dms_out, float* poses_out, void* stream) {
+  if (!h || !dms || !poses || !cfgs || !coms || !cossin || !edge_ratio || !dms_out || !poses_out || B < 1 || hw < 2 || J < 1) return DR_ERR_ARG;
+  h->launches += launch_data_aug(B, hw, J, dms, poses, cfgs, coms, cossin, edge_ratio, dms_out, poses_out, (cudaStream_t)stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return DR_OK;
+}
+
 int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {
   const bool reuse = (precision & 0x100) != 0 && h && h->wk; precision &= 0xff;
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;

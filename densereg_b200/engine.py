@@ -154,6 +154,14 @@ class DenseRegEngine:
                                               _ptr(coms), self._stream()))
         return dms, cfgs, coms
 
+    def data_aug(self, dms, poses, cfgs, coms, cossin, edge_ratio):
+        """data/preprocess.py data_aug with caller-drawn randomness: cossin (B,2), edge_ratio (B,2) [h, w]."""
+        B, hw = dms.shape[0], dms.shape[1]
+        dms_out = torch.empty_like(dms); poses_out = torch.empty_like(poses)
+        self._check(self.lib.dr_data_aug(self._h, B, hw, poses.shape[1] // 3, _ptr(dms), _ptr(poses), _ptr(cfgs), _ptr(coms), _ptr(cossin),
+                                         _ptr(edge_ratio), _ptr(dms_out), _ptr(poses_out), self._stream()))
+        return dms_out, poses_out
+
     def zero_grads(self):
         self._check(self.lib.dr_zero_grads(self._h, self._stream()))
 

@@ -179,6 +179,16 @@ class JointDetectionModel:
         return ck["step"]
 
 
+def augment(engine, tens, rng):
+    """data_aug (data/preprocess.py:234-267): angle ~ U(-pi,pi), edge_ratio = clip(N(1,0.2),0.9,1.1); draws on the host, warp on the GPU."""
+    dms, poses, cfgs, coms = tens
+    B = dms.shape[0]
+    ang = rng.uniform(-np.pi, np.pi, size=B).astype(np.float32)
+    cossin = torch.from_numpy(np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)).to(dms.device)
+    er = torch.from_numpy(np.clip(rng.normal(1.0, 0.2, size=(B, 2)), 0.9, 1.1).astype(np.float32)).to(dms.device)
+    return engine.data_aug(dms, poses, cfgs, coms, cossin, er)
+
+
 def shard_batch(batch_size, rank, world):
     """tf.split of the global minibatch across towers (train_multi_gpu.py:63-64) -> [lo, hi) of this rank."""
     per = batch_size // world
@@ -201,11 +211,14 @@ def train(model, rank=0, world=1, log=print):
     lo, hi = shard_batch(f.batch_size, rank, world)
     dev = eng.device
     t_log = time.time()
+    rng = np.random.RandomState(1234 + rank)
     for step in range(max_steps):
         eng.zero_grads()                                                           # reset_op :139
         for sub in range(f.sub_batch):                                             # :140-148
             dms, poses, cfgs, coms, _ = model.train_dataset.batch(f.batch_size, seed=step * f.sub_batch + sub)
             tens = [torch.from_numpy(a[lo:hi]).pin_memory().to(dev, non_blocking=True) for a in (dms, poses, cfgs, coms)]
+            if f.is_aug:                                                               # hourglass_um_crop_tiny.py:333-334
+                tens[0], tens[1] = augment(eng, tens, rng)
             loss = model.loss(*tens, dropout_seed=(step * f.sub_batch + sub) * world + rank)
         allreduce_gradients(eng.grads, world)
         eng.optimizer_step(step + 1, model.lr_at(step), accum_steps=f.sub_batch, world=world)   # train_op :150

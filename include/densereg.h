@@ -150,6 +150,13 @@ DR_API int dr_crop_from_xyz_pose(dr_handle* h, int B, int in_h, int in_w, const 
 DR_API int dr_crop_from_bbx(dr_handle* h, int B, int in_h, int in_w, const float* frames, const float* bbx, const float* cfg_host6,
                             int out_hw, float* dm_out, float* cfg_out, float* com_out, void* stream);
 
+/* Training-time augmentation ("next" row 8f-3): data/preprocess.py:234-267 data_aug on a batch of crops.
+ * dms (B,hw,hw,1), poses (B,3J), cfgs (B,6), coms (B,3); cossin (B,2) = cos/sin of the rotation angle ~ U(-pi,pi) and
+ * edge_ratio (B,2) = clip(N(1,0.2),0.9,1.1) [height, width] are drawn by the CALLER (TF's RNG stream is not reproducible).
+ * Outputs dms_out (B,hw,hw,1), poses_out (B,3J). */
+DR_API int dr_data_aug(dr_handle* h, int B, int hw, int J, const float* dms, const float* poses, const float* cfgs, const float* coms,
+                       const float* cossin, const float* edge_ratio, float* dms_out, float* poses_out, void* stream);
+
 /* per-conv debug entry used by the parity tests: runs ONE conv of the table on caller data.
  * x (B,H,W,cin) dense -> y (B,Ho,Wo,cout) = conv(x, W[idx]) (no BRN/bias/activation). */
 DR_API int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream);

@@ -83,3 +83,65 @@ def center_of_mass(crop, cfg):
     ave_d = np.maximum(ave_d, f32(200.0)) if pos.size else f32(200.0)   # tf.maximum(nan, 200) is nan in TF; empty crops are degenerate
     ave_u, ave_v = f32(c_w / 2), f32(c_h / 2)
     return np.array([(ave_u - cfg[2]) * ave_d / cfg[0], (ave_v - cfg[3]) * ave_d / cfg[1], ave_d], f32)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# data augmentation: data/preprocess.py:234-267 data_aug
+# --------------------------------------------------------------------------------------------------------------------
+def _rotate_nearest(img, cost, sint):
+    """tf.contrib.image.rotate(dm, angle) with the default NEAREST interpolation (TF 1.x contrib/image):
+    angles_to_projective_transforms -> [cos, -sin, x_off, sin, cos, y_off, 0, 0] maps OUTPUT (x,y) to INPUT (x',y'),
+    sampled at (round(y'), round(x')) (std::round, half away from zero) with zero fill."""
+    h, w = img.shape
+    cost, sint = f32(cost), f32(sint)
+    x_off = ((f32(w - 1) - (cost * f32(w - 1) - sint * f32(h - 1))) / f32(2.0)).astype(f32)
+    y_off = ((f32(h - 1) - (sint * f32(w - 1) + cost * f32(h - 1))) / f32(2.0)).astype(f32)
+    xo = np.arange(w, dtype=f32)[None, :]; yo = np.arange(h, dtype=f32)[:, None]
+    xi = ((cost * xo + (-sint) * yo).astype(f32) + x_off).astype(f32)
+    yi = ((sint * xo + cost * yo).astype(f32) + y_off).astype(f32)
+    rx = np.where(xi >= 0, np.floor(xi + f32(0.5)), np.ceil(xi - f32(0.5))).astype(np.int64)
+    ry = np.where(yi >= 0, np.floor(yi + f32(0.5)), np.ceil(yi - f32(0.5))).astype(np.int64)
+    ok = (rx >= 0) & (rx < w) & (ry >= 0) & (ry < h)
+    out = np.zeros_like(img)
+    out[ok] = img[ry[ok], rx[ok]]
+    return out
+
+
+def _resize_nearest(img, out_h, out_w):
+    """tf.image.resize_images(method=1) == ResizeNearestNeighbor, align_corners=False: src = min(floor(dst*in/out), in-1)."""
+    in_h, in_w = img.shape
+    ys = np.minimum(np.floor(np.arange(out_h, dtype=f32) * (f32(in_h) / f32(out_h))).astype(np.int64), in_h - 1)
+    xs = np.minimum(np.floor(np.arange(out_w, dtype=f32) * (f32(in_w) / f32(out_w))).astype(np.int64), in_w - 1)
+    return img[ys][:, xs]
+
+
+def _crop_or_pad(img, th, tw):
+    """tf.image.resize_image_with_crop_or_pad: centred crop / zero pad with floor-division offsets."""
+    h, w = img.shape
+    wd, hd = tw - w, th - h
+    oc_w, op_w = max(-wd // 2, 0), max(wd // 2, 0)
+    oc_h, op_h = max(-hd // 2, 0), max(hd // 2, 0)
+    c = img[oc_h:oc_h + min(th, h), oc_w:oc_w + min(tw, w)]
+    out = np.zeros((th, tw), img.dtype)
+    out[op_h:op_h + c.shape[0], op_w:op_w + c.shape[1]] = c
+    return out
+
+
+def data_aug(dm, pose, cfg, com, cost, sint, edge_ratio):
+    """One element of data_aug's map_fn.  dm (h,w) mm, pose (3J,) mm, cfg (6,), com (3,); the random draws of the reference
+    (angle ~ U(-pi,pi) -> cost, sint; edge_ratio = clip(N(1,0.2),0.9,1.1) (2,)) are INPUTS so that the result is reproducible."""
+    dm = np.asarray(dm, f32); pose = np.asarray(pose, f32).reshape(-1, 3); cfg = np.asarray(cfg, f32); com = np.asarray(com, f32)
+    er = np.asarray(edge_ratio, f32); cost, sint = f32(cost), f32(sint)
+    h, w = dm.shape
+    rot = _rotate_nearest(dm, cost, sint)
+    th, tw = int(f32(h) * er[0]), int(f32(w) * er[1])                       # tf.to_int32(tf.to_float(shape)*edge_ratio) :253-254
+    out = _crop_or_pad(_resize_nearest(rot, th, tw), h, w)
+    # pose: rotate / stretch in uvd about the projected centre of mass (:241-247, :258-262)
+    ucom = (com[0] * cfg[0]) / com[2] + cfg[2]; vcom = (com[1] * cfg[1]) / com[2] + cfg[3]
+    u = ((pose[:, 0] * cfg[0]) / pose[:, 2] + cfg[2]) - ucom
+    v = ((pose[:, 1] * cfg[1]) / pose[:, 2] + cfg[3]) - vcom
+    d = pose[:, 2] - com[2]
+    ur = (u * cost + v * sint).astype(f32); vr = (u * (-sint) + v * cost).astype(f32)          # row-vector @ rot_mat
+    ur = (ur * er[1] + ucom).astype(f32); vr = (vr * er[0] + vcom).astype(f32); dr = (d + com[2]).astype(f32)
+    x = ((ur - cfg[2]) * dr / cfg[0]).astype(f32); y = ((vr - cfg[3]) * dr / cfg[1]).astype(f32)   # util.py:21 _bpro
+    return out, np.stack([x, y, dr], axis=1).reshape(-1).astype(f32)

@@ -77,3 +77,35 @@ def test_gpu_frames_to_xyz_pipeline(built_lib):
     xyz = eng.infer(dms, cfgs, coms)
     torch.cuda.synchronize()
     assert xyz.shape == (4, 48) and torch.isfinite(xyz).float().mean() > 0.9
+
+
+def test_oracle_data_aug_properties():
+    dms, poses, cfgs, coms = synth.make_batch(2, 16, seed=0)
+    o, p = C.data_aug(dms[0, :, :, 0], poses[0], cfgs[0], coms[0], 1.0, 0.0, [1.0, 1.0])
+    assert np.array_equal(o, dms[0, :, :, 0]) and np.abs(p - poses[0]).max() < 1e-4              # identity
+    a = 0.7
+    o, p = C.data_aug(dms[0, :, :, 0], poses[0], cfgs[0], coms[0], np.float32(np.cos(a)), np.float32(np.sin(a)), [1.08, 0.93])
+    pp = p.reshape(-1, 3); u = pp[:, 0] * cfgs[0, 0] / pp[:, 2] + cfgs[0, 2]; v = pp[:, 1] * cfgs[0, 1] / pp[:, 2] + cfgs[0, 3]
+    ui = np.clip(np.round(u).astype(int), 0, 127); vi = np.clip(np.round(v).astype(int), 0, 127)
+    assert (o[vi, ui] > 0).mean() > 0.9          # image warp and pose warp agree: the joints still sit on the hand
+    assert np.array_equal(C._crop_or_pad(np.ones((130, 120), np.float32), 128, 128).sum(), 128 * 120)
+
+
+@pytest.mark.gpu
+def test_gpu_data_aug_matches_oracle(built_lib):
+    from densereg_b200.engine import DenseRegEngine
+    B, J = 6, 16
+    eng = DenseRegEngine(1, 64, J, max_batch=1, training=False)
+    dms, poses, cfgs, coms = synth.make_batch(B, J, seed=4)
+    rng = np.random.RandomState(0)
+    ang = rng.uniform(-np.pi, np.pi, B).astype(np.float32); ang[0] = 0.0
+    cs = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    er = np.clip(rng.normal(1.0, 0.2, (B, 2)), 0.9, 1.1).astype(np.float32); er[0] = 1.0; er[1] = [1.1, 0.9]; er[2] = [0.9, 1.1]
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    do, po = eng.data_aug(cu(dms), cu(poses), cu(cfgs), cu(coms), cu(cs), cu(er))
+    torch.cuda.synchronize()
+    do, po = do.cpu().numpy(), po.cpu().numpy()
+    for b in range(B):
+        o, p = C.data_aug(dms[b, :, :, 0], poses[b], cfgs[b], coms[b], cs[b, 0], cs[b, 1], er[b])
+        assert np.array_equal(do[b, :, :, 0], o), "augmented crop %d not bit-exact" % b
+        np.testing.assert_allclose(po[b], p, rtol=1e-5, atol=1e-3)
