@@ -303,6 +303,10 @@ bool conv_tc_eligible(const ConvProblem& p) {
   if ((reinterpret_cast<uintptr_t>(p.w_kmajor) & 15) != 0) return false;
   if (p.Cout < 8) return false;
   if (p.pad_t != (p.k - 1) / 2 || p.pad_l != p.pad_t) return false;
+  // tiny problems are latency-bound on the TMA/mbarrier pipeline (~18 us floor); below the threshold the FFMA kernel is used
+  static double min_mmac = -1.0;
+  if (min_mmac < 0) { const char* e = getenv("DENSEREG_TC_MIN_MMAC"); min_mmac = e ? atof(e) : 0.0; }
+  if (min_mmac > 0 && (double)p.B * p.H * p.W * p.k * p.k * p.Cin * p.Cout < min_mmac * 1e6) return false;
   return true;
 }
 

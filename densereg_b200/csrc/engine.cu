@@ -85,6 +85,12 @@ struct dr_handle {
   cudaStream_t wgrad_stream = nullptr;
   cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr}, ev_wdone[3] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool side_stream = true;
+  // inference CUDA graph (dr_config.reserved[0] != 0): the ~170 launches of dr_infer are captured once per (batch, pointers) key
+  // on an internal stream and replayed with cudaGraphLaunch on the caller's stream -> B=1 latency is no longer launch-bound
+  struct InferGraph { int B = 0; const void *dm = nullptr, *cfg = nullptr, *com = nullptr; void *xyz = nullptr, *top5 = nullptr;
+                      cudaGraphExec_t exec = nullptr; int warm = 0; };
+  InferGraph infer_graph;
+  cudaStream_t capture_stream = nullptr;
 };
 
 namespace {
@@ -695,6 +701,8 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
 
 int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
+  if (h->infer_graph.exec) cudaGraphExecDestroy(h->infer_graph.exec);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
   for (int i = 0; i < 3; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_wdone[i]) cudaEventDestroy(h->ev_wdone[i]); }
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -796,10 +804,8 @@ int dr_vote(dr_handle* h, int B, int H, int W, int J,
   return DR_OK;
 }
 
-int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const float* coms,
-             float* xyz_mm, int32_t* top5_idx, void* stream) {
-  if (!h || !dm_mm || !cfgs || !coms || !xyz_mm) return DR_ERR_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
+static int infer_enqueue(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const float* coms, float* xyz_mm, int32_t* top5_idx,
+                         cudaStream_t st) {
   int rc = forward_impl(h, B, dm_mm, coms, 0, 0, 0, st);
   if (rc) return rc;
   Exec X{h, B, st};
@@ -807,6 +813,49 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
   h->launches += launch_vote(B, OUT, OUT, J, X.ptr(h->v_hm[s]), X.cs(h->v_hm[s]), X.ptr(h->v_hm3[s]), X.cs(h->v_hm3[s]),
                              X.ptr(h->v_um[s]), X.cs(h->v_um[s]), X.ptr(X.whole(h->buf_tiny)), cfgs, coms, xyz_mm, top5_idx,
                              h->clamp_dev, st);
+  return DR_OK;
+}
+
+int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const float* coms,
+             float* xyz_mm, int32_t* top5_idx, void* stream) {
+  if (!h || !dm_mm || !cfgs || !coms || !xyz_mm) return DR_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.reserved[0] == 0) {                          // eager
+    int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaGetLastError());
+    return DR_OK;
+  }
+  dr_handle::InferGraph& g = h->infer_graph;
+  const bool same = g.B == B && g.dm == dm_mm && g.cfg == cfgs && g.com == coms && g.xyz == xyz_mm && g.top5 == top5_idx;
+  if (!same) {                                            // new key: drop the old graph, run eagerly once (allocations, attributes)
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    g.B = B; g.dm = dm_mm; g.cfg = cfgs; g.com = coms; g.xyz = xyz_mm; g.top5 = top5_idx; g.warm = 0;
+  }
+  if (!g.exec && g.warm >= 1) {                           // second call with the same key: capture
+    if (!h->capture_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamSynchronize(st));               // the eager warm-up on `st` is done before the internal stream touches the arena
+    CUDA_TRY(h, cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, h->capture_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.warm = -1000000;                                  // capture failed: stay eager for this key
+    } else {
+      ce = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.warm = -1000000; }
+    }
+  }
+  if (g.exec) {
+    CUDA_TRY(h, cudaGraphLaunch(g.exec, st));
+    return DR_OK;
+  }
+  ++g.warm;
+  int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, st);
+  if (rc) return rc;
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }

@@ -204,7 +204,8 @@ def allreduce_gradients(grads, world):
 
 
 def train(model, rank=0, world=1, log=print):
-    """model/train_single_gpu.py:37-177 (loop :138-175) with per-rank sharding of each micro-batch."""
+    """model/train_single_gpu.py:37-177 (loop :138-175) with per-rank sharding of each micro-batch.  Writes the reference's
+    `training_log.txt` (:135-158) and `validation_log.txt` (hourglass_um_crop_tiny.py:126,816-840) under train_dir."""
     f = model.flags
     eng = model.engine
     max_steps = f.max_steps or model.max_steps
@@ -212,6 +213,11 @@ def train(model, rank=0, world=1, log=print):
     dev = eng.device
     t_log = time.time()
     rng = np.random.RandomState(1234 + rank)
+    tlog = vlog = None
+    if rank == 0:
+        os.makedirs(model.train_dir, exist_ok=True)
+        tlog = open(os.path.join(model.train_dir, "training_log.txt"), "a")
+        vlog = open(os.path.join(model.train_dir, "validation_log.txt"), "a")
     for step in range(max_steps):
         eng.zero_grads()                                                           # reset_op :139
         for sub in range(f.sub_batch):                                             # :140-148
@@ -226,10 +232,18 @@ def train(model, rank=0, world=1, log=print):
             lv = loss.cpu().numpy()
             assert not np.isnan(lv[0]), "Model diverged with loss = NaN"         # :147
             dt = time.time() - t_log; t_log = time.time()
-            log("step %d, loss = %.2f (hm %.2f hm3 %.2f um %.2f reg %.3f) lr %.1e, %.3f sec/5 steps"
-                % (step, lv[0], lv[1], lv[2], lv[3], lv[4], model.lr_at(step), dt))
+            msg = ("step %d, loss = %.2f (hm %.2f hm3 %.2f um %.2f reg %.3f) lr %.1e, %.3f sec/5 steps"
+                   % (step, lv[0], lv[1], lv[2], lv[3], lv[4], model.lr_at(step), dt))
+            log(msg); tlog.write(msg + "\n"); tlog.flush()
+        if step % 40 == 0 and rank == 0 and model.is_validate:                     # do_test every 40 steps :165-166
+            vd, vp, vc, vm, _ = model.val_dataset.batch(3, seed=900_000 + step)    # batch of 3 like the reference (:62-65)
+            xyz = model.test(*[torch.from_numpy(a).to(dev) for a in (vd, vc, vm)]).cpu().numpy()
+            err = [meanJntError(x, g) for x, g in zip(xyz, vp)]
+            vlog.write("step %d mean joint error (mm): %s\n" % (step, " ".join("%.3f" % e for e in err))); vlog.flush()
         if (step + 1) % 100 == 0 and rank == 0:                                    # :168-175
             model.save(step + 1)
+    if rank == 0:
+        tlog.close(); vlog.close()
     return max_steps
 
 

@@ -56,7 +56,7 @@ typedef struct {
   int32_t max_batch;     /* workspace is sized for this  */
   int32_t precision;     /* dr_precision                 */
   int32_t device;        /* CUDA ordinal                 */
-  int32_t reserved[7];
+  int32_t reserved[7];   /* reserved[0] != 0: dr_infer replays a CUDA graph captured per (batch, pointer) key */
 } dr_config;
 
 typedef struct dr_handle dr_handle;

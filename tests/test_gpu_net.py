@@ -221,3 +221,23 @@ def test_training_overfits_small_batch(built_lib, precision):
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < 0.5 * losses[0] and losses[2] < losses[0], losses      # measured: 9051 -> 2906 (fp32), monotone
     dump("overfit_%s.json" % precision, {"losses": losses})
+
+
+def test_infer_cuda_graph_matches_eager(built_lib):
+    """dr_config.reserved[0]: dr_infer replayed from a captured CUDA graph gives bit-identical xyz and tracks input updates."""
+    from densereg_b200.engine import DenseRegEngine
+    from densereg_b200 import synth
+    kw = dict(num_stack=1, num_fea=64, num_jnt=16, max_batch=3, training=False, precision="tf32x3")
+    eager, graph = DenseRegEngine(**kw), DenseRegEngine(infer_graph=True, **kw)
+    eager.init_params(0, 0.05); graph.load_flat(eager.params, eager.state)
+    d, po, cf, co = [cu(a) for a in synth.make_batch(3, 16, seed=8)]
+    ref = eager.infer(d, cf, co).clone()
+    out = torch.empty_like(ref)
+    for _ in range(4):                       # eager warm-up, capture, replay, replay
+        graph.infer(d, cf, co, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    d2 = cu(synth.make_batch(3, 16, seed=9)[0]); d.copy_(d2)          # same buffer, new contents -> replay must see them
+    ref2 = eager.infer(d, cf, co).clone()
+    graph.infer(d, cf, co, out=out); torch.cuda.synchronize()
+    assert torch.equal(out, ref2) and not torch.equal(ref, ref2)

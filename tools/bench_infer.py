@@ -9,14 +9,15 @@ import torch
 ap = argparse.ArgumentParser()
 ap.add_argument("--precision", default="tf32x3"); ap.add_argument("--jnt", type=int, default=21)
 ap.add_argument("--batches", default="1,8,64,256"); ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--graph", type=int, default=1)
 ap.add_argument("--check", type=int, default=2, help="crops compared with the CPU oracle (0 = skip)")
 a = ap.parse_args()
 from densereg_b200.engine import DenseRegEngine
 from densereg_b200 import synth
 Bs = [int(x) for x in a.batches.split(",")]
-eng = DenseRegEngine(2, 128, a.jnt, max_batch=max(Bs), precision=a.precision, training=False)
+eng = DenseRegEngine(2, 128, a.jnt, max_batch=max(Bs), precision=a.precision, training=False, infer_graph=bool(a.graph))
 eng.init_params(0, 0.05)
-out = {"workload": "MSRA-shape J=%d 2-stack fea=128 inference (forward + vote), %s" % (a.jnt, a.precision), "rows": []}
+out = {"workload": "MSRA-shape J=%d 2-stack fea=128 inference (forward + vote), %s, cuda_graph=%d" % (a.jnt, a.precision, a.graph), "rows": []}
 for B in Bs:
     dms, poses, cfgs, coms = synth.make_batch(min(B, 64), a.jnt, seed=B)
     rep = (B + dms.shape[0] - 1) // dms.shape[0]
@@ -36,8 +37,8 @@ for B in Bs:
     res = torch.empty(B, 3 * a.jnt).pin_memory()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(a.iters):
-        dd, cc, oo = [t.to("cuda", non_blocking=True) for t in hd]
-        eng.infer(dd, cc, oo, out=xyz)
+        d.copy_(hd[0], non_blocking=True); cf.copy_(hd[1], non_blocking=True); co.copy_(hd[2], non_blocking=True)   # same device buffers
+        eng.infer(d, cf, co, out=xyz)
         res.copy_(xyz, non_blocking=True)
     torch.cuda.synchronize(); ms_e2e = (time.perf_counter() - t0) * 1e3 / a.iters
     out["rows"].append({"batch": B, "ms": ms, "crops_per_s": B / ms * 1e3, "e2e_crops_per_s": B / ms_e2e * 1e3,
