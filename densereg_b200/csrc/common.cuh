@@ -82,15 +82,9 @@ int launch_upadd_bwd_lo(int B, int H, int W, int C, const float* dy, int dy_cs, 
 int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* dst, int dst_cs, int accumulate,
                      const float* tiny_mask, cudaStream_t st);
 int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st);
-int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums /*2C, pre-zeroed*/, cudaStream_t st);
 // stats + finalize in ONE launch (last block finalizes); counter must be zero on entry
 int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, double* sums, unsigned int* counter,
                                   const float* beta_gamma, float* state, float* aff, float* bstat, int update_state, cudaStream_t st);
-// BRN finalize (train): sums -> mean/var, r, d, affine a,b; optional state update. bstat: mean,inv_std,r,d [C each]
-int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
-                        float* aff, float* bstat, int update_state, cudaStream_t st);
-// eval fold: aff = {scale, shift} from moving stats (or {1,bias})
-int launch_fold_affine(int C, int brn, const float* pbeta_gamma_or_bias, const float* state, float* aff, cudaStream_t st);
 // y = act(raw*a+b) (+res)
 int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
                      const float* res, int res_cs, float* y, int y_cs, cudaStream_t st);
@@ -122,7 +116,6 @@ int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, 
 int launch_finish_loss(const double* acc /*hm,hm3,um,reg*/, float* out5, cudaStream_t st);
 int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
                 float lr_t, float b1, float b2, float eps, cudaStream_t st);
-int launch_transpose_weights(int k, int cin, int cout, const float* w, float* wt, cudaStream_t st);
 int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st);
 int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, float* dst, cudaStream_t st);
 

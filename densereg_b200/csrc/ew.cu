@@ -160,29 +160,7 @@ __global__ void fill_view_kernel(size_t npix, int C, float* __restrict__ dst, in
   }
 }
 
-// per-channel sum / sum of squares in double.  block (32 channels, 8 pixel lanes); grid (C/32, pixel blocks)
-__global__ void channel_stats_kernel(size_t npix, int C, const float* __restrict__ x, int x_cs, double* __restrict__ sums) {
-  __shared__ double s1[8][33], s2[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
-      float v = x[p * x_cs + c];
-      a += (double)v; b += (double)v * (double)v;
-    }
-  }
-  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    atomicAdd(sums + c, a); atomicAdd(sums + C + c, b);
-  }
-}
 
-__global__ void brn_finalize_kernel(int C, double n, const double* __restrict__ sums, const float* __restrict__ bg,
-                                    float* __restrict__ state, float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
-  brn_finalize_dev<0, 256>(threadIdx.x, C, n, sums, bg, state, aff, bstat, update_state);
-}
 
 // per-channel sum / sum of squares in double + BRN finalize by the LAST block to finish (one launch instead of two)
 __global__ void channel_stats_finalize_kernel(size_t npix, int C, const float* __restrict__ x, int x_cs, double* __restrict__ sums,
@@ -214,16 +192,6 @@ __global__ void channel_stats_finalize_kernel(size_t npix, int C, const float* _
   }
 }
 
-__global__ void fold_affine_kernel(int C, int brn, const float* __restrict__ pb, const float* __restrict__ state, float* __restrict__ aff) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (brn) {                                                                   // ops.py:173-180
-    float inv = (1.0f / sqrtf(state[C + c] + 0.001f)) * pb[C + c];
-    aff[c] = inv; aff[C + c] = pb[c] - state[c] * inv;
-  } else {
-    aff[c] = 1.0f; aff[C + c] = pb[c];
-  }
-}
 
 __global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ raw, int raw_cs, const float* __restrict__ aff,
                                  int relu, const float* __restrict__ res, int res_cs, float* __restrict__ y, int y_cs) {
@@ -530,14 +498,6 @@ __global__ void adam_kernel(size_t n, float* __restrict__ p, const float* __rest
   }
 }
 
-// wt[(kk-1-tap)][n][c] = w[tap][c][n] : 180-degree rotated, in/out swapped (dgrad == forward conv with wt)
-__global__ void transpose_weights_kernel(int kk, int cin, int cout, const float* __restrict__ w, float* __restrict__ wt) {
-  size_t n = (size_t)kk * cin * cout;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % cin); size_t r = i / cin; int o = (int)(r % cout); int tap = (int)(r / cout);
-    wt[i] = w[((size_t)(kk - 1 - tap) * cin + c) * cout + o];
-  }
-}
 
 __global__ void init_trunc_normal_kernel(size_t n, float* __restrict__ p, float stddev, uint64_t seed) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -621,23 +581,10 @@ static dim3 stats_grid(size_t npix, int C) {
   if (gy < 1) gy = 1;
   return dim3(gx, (unsigned)gy);
 }
-int launch_channel_stats(size_t npix, int C, const float* x, int x_cs, double* sums, cudaStream_t st) {
-  channel_stats_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums);
-  return 1;
-}
 int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, double* sums, unsigned int* counter,
                                   const float* beta_gamma, float* state, float* aff, float* bstat, int update_state, cudaStream_t st) {
   channel_stats_finalize_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums, counter, beta_gamma, state, aff, bstat,
                                                                             update_state);
-  return 1;
-}
-int launch_brn_finalize(int C, double n, const double* sums, const float* beta_gamma, float* state,
-                        float* aff, float* bstat, int update_state, cudaStream_t st) {
-  brn_finalize_kernel<<<1, 256, 0, st>>>(C, n, sums, beta_gamma, state, aff, bstat, update_state);
-  return 1;
-}
-int launch_fold_affine(int C, int brn, const float* pb, const float* state, float* aff, cudaStream_t st) {
-  fold_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, brn, pb, state, aff);
   return 1;
 }
 int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
@@ -730,11 +677,6 @@ int launch_finish_loss(const double* acc, float* out5, cudaStream_t st) {
 int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
                 float lr_t, float b1, float b2, float eps, cudaStream_t st) {
   adam_kernel<<<blocks_for(n, EW_T * 4, 148 * 8), EW_T, 0, st>>>(n, p, g, m, v, inv_scale, clip, lr_t, b1, b2, eps);
-  return 1;
-}
-int launch_transpose_weights(int k, int cin, int cout, const float* w, float* wt, cudaStream_t st) {
-  size_t n = (size_t)k * k * cin * cout;
-  transpose_weights_kernel<<<blocks_for(n), EW_T, 0, st>>>(k * k, cin, cout, w, wt);
   return 1;
 }
 int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st) {
