@@ -9,8 +9,10 @@
   data/evaluation.py:9-18                 maxJntError/meanJntError -> evaluation helpers below
 
 All arithmetic happens in libdensereg_sm100.so through DenseRegEngine; this file only moves buffers,
-steps counters and writes text.  Datasets: none are on the box, so the dataset objects
-here generate seeded synthetic crops of each dataset's shape (densereg_b200/synth.py).
+steps counters and writes text.  Datasets: the TFRecord shards of data/{icvl,nyu,msra}.py are read by
+densereg_b200/datasets.py when they exist under the reference's directories (`--data_source tfrecord|auto`); none are on
+the box, so by default SyntheticDataset generates seeded synthetic crops of each dataset's shape
+(densereg_b200/synth.py).  Both kinds expose `batch_device(engine, batch_size, seed, lo, hi)`.
 """
 import argparse
 import os
@@ -19,7 +21,7 @@ import time
 import numpy as np
 import torch
 
-from . import synth
+from . import datasets, synth
 from .engine import DenseRegEngine
 
 
@@ -47,6 +49,9 @@ def build_argparser():
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "tf32", "tf32x3"])
     p.add_argument("--max_steps", type=int, default=0, help="stop after this many optimiser steps (0 = epoch schedule)")
     p.add_argument("--test_num", type=int, default=0, help="number of synthetic test frames (0 = dataset's exact_num)")
+    p.add_argument("--data_source", type=str, default="auto", choices=["auto", "synthetic", "tfrecord"],
+                   help="tfrecord = the reference's shards under --data_dir; auto = tfrecord when every shard exists, else synthetic")
+    p.add_argument("--data_dir", type=str, default=None, help="dataset root (default: the reference's ./exp/data/<dataset>/)")
     return p
 
 
@@ -69,6 +74,12 @@ class SyntheticDataset:
         names = ["%s_seq/image_%06d.png" % (self.subset, self._cursor + i) for i in range(batch_size)]
         self._cursor += batch_size
         return dms, poses, cfgs, coms, names
+
+    def batch_device(self, engine, batch_size, seed=0, lo=0, hi=None):
+        """Rows [lo,hi) of the global batch as device tensors (same contract as datasets.BaseDataset.batch_device)."""
+        dms, poses, cfgs, coms, names = self.batch(batch_size, seed)
+        tens = [torch.from_numpy(a[lo:hi]).pin_memory().to(engine.device, non_blocking=True) for a in (dms, poses, cfgs, coms)]
+        return tens[0], tens[1], tens[2], tens[3], names[lo:hi]
 
 
 def meanJntError(skel1, skel2):      # data/evaluation.py:15-18
@@ -134,7 +145,7 @@ class JointDetectionModel:
     @property
     def lr_decay_factor(self): return self._lr_decay_factor
     @property
-    def decay_steps(self): return int(self._num_batches_per_epoch * self._num_epochs_per_decay[self._dataset.name])
+    def decay_steps(self): return int(self._num_batches_per_epoch * self._num_epochs_per_decay[self.flags.dataset])
     @property
     def max_steps(self): return self._max_steps
     @property
@@ -221,8 +232,7 @@ def train(model, rank=0, world=1, log=print):
     for step in range(max_steps):
         eng.zero_grads()                                                           # reset_op :139
         for sub in range(f.sub_batch):                                             # :140-148
-            dms, poses, cfgs, coms, _ = model.train_dataset.batch(f.batch_size, seed=step * f.sub_batch + sub)
-            tens = [torch.from_numpy(a[lo:hi]).pin_memory().to(dev, non_blocking=True) for a in (dms, poses, cfgs, coms)]
+            tens = list(model.train_dataset.batch_device(eng, f.batch_size, seed=step * f.sub_batch + sub, lo=lo, hi=hi)[:4])
             if f.is_aug:                                                               # hourglass_um_crop_tiny.py:333-334
                 tens[0], tens[1] = augment(eng, tens, rng)
             loss = model.loss(*tens, dropout_seed=(step * f.sub_batch + sub) * world + rank)
@@ -236,9 +246,12 @@ def train(model, rank=0, world=1, log=print):
                    % (step, lv[0], lv[1], lv[2], lv[3], lv[4], model.lr_at(step), dt))
             log(msg); tlog.write(msg + "\n"); tlog.flush()
         if step % 40 == 0 and rank == 0 and model.is_validate:                     # do_test every 40 steps :165-166
-            vd, vp, vc, vm, _ = model.val_dataset.batch(3, seed=900_000 + step)    # batch of 3 like the reference (:62-65)
-            xyz = model.test(*[torch.from_numpy(a).to(dev) for a in (vd, vc, vm)]).cpu().numpy()
-            err = [meanJntError(x, g) for x, g in zip(xyz, vp)]
+            try:                                                                   # batch of 3 like the reference (:62-65)
+                vd, vp, vc, vm, _ = model.val_dataset.batch_device(eng, 3, seed=900_000 + step)
+            except datasets.EndOfData:
+                continue
+            xyz = model.test(vd, vc, vm).cpu().numpy()
+            err = [meanJntError(x, g) for x, g in zip(xyz, vp.cpu().numpy())]
             vlog.write("step %d mean joint error (mm): %s\n" % (step, " ".join("%.3f" % e for e in err))); vlog.flush()
         if (step + 1) % 100 == 0 and rank == 0:                                    # :168-175
             model.save(step + 1)
@@ -258,9 +271,12 @@ def test(model, out_path=None, log=print):
     dev = model.engine.device
     with open(out_path, "w") as fo:
         while n < total:
-            dms, poses, cfgs, coms, names = ds.batch(f.batch_size, seed=10_000 + step)
-            xyz = model.test(*[torch.from_numpy(a).to(dev) for a in (dms, cfgs, coms)]).cpu().numpy()
-            for xyz_val, gt_val, name in zip(xyz, poses, names):
+            try:
+                dms, poses, cfgs, coms, names = ds.batch_device(model.engine, f.batch_size, seed=10_000 + step)
+            except datasets.EndOfData:                                             # OutOfRangeError ends the loop, test_model.py:64
+                break
+            xyz = model.test(dms, cfgs, coms).cpu().numpy()
+            for xyz_val, gt_val, name in zip(xyz, poses.cpu().numpy(), names):
                 errs.append(meanJntError(xyz_val, gt_val)); maxs.append(maxJntError(xyz_val, gt_val))
                 fo.write(format_result_row(name, xyz_val))
                 n += 1
@@ -273,6 +289,21 @@ def test(model, out_path=None, log=print):
     return float(np.nanmean(errs)), float(np.nanmean(maxs))
 
 
+def open_datasets(flags, log=print):
+    """The dataset switch of hourglass_um_crop_tiny.py:886-906: (train_dataset, val_dataset)."""
+    subset = "training" if flags.is_train else "testing"
+    if flags.data_source != "synthetic":
+        real = [datasets.open_dataset(flags.dataset, s, flags.pid, flags.data_dir) for s in (subset, "testing")]
+        if all(d.available() for d in real):
+            log("[densereg_b200] reading TFRecord shards from %s" % real[0].tf_dir)
+            return real[0], real[1]
+        if flags.data_source == "tfrecord":
+            missing = [p for d in real for p in d.filenames if not os.path.exists(p)]
+            raise FileNotFoundError("TFRecord shards missing (first: %s)" % missing[0])
+        log("[densereg_b200] no TFRecord shards under %s -- using synthetic %s-shaped crops" % (real[0].tf_dir, flags.dataset))
+    return SyntheticDataset(flags.dataset, subset, flags.pid), SyntheticDataset(flags.dataset, "testing", flags.pid)
+
+
 def main(argv=None):
     flags = build_argparser().parse_args(argv)
     if flags.net_module != "um_v1":
@@ -281,8 +312,7 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ds = SyntheticDataset(flags.dataset, "training" if flags.is_train else "testing", flags.pid)
-    val = SyntheticDataset(flags.dataset, "testing", flags.pid)
+    ds, val = open_datasets(flags)
     model = JointDetectionModel(ds, flags, val_dataset=val, device=local, world=world)
     model.engine.init_params(seed=0)
     if flags.is_train:
