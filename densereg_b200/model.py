@@ -21,7 +21,7 @@ import time
 import numpy as np
 import torch
 
-from . import datasets, synth
+from . import datasets, synth, tf_checkpoint
 from .engine import DenseRegEngine
 
 
@@ -49,6 +49,8 @@ def build_argparser():
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "tf32", "tf32x3"])
     p.add_argument("--max_steps", type=int, default=0, help="stop after this many optimiser steps (0 = epoch schedule)")
     p.add_argument("--test_num", type=int, default=0, help="number of synthetic test frames (0 = dataset's exact_num)")
+    p.add_argument("--restore_step", type=int, default=None,
+                   help="checkpoint step to restore from train_dir (testing defaults to -1 like run_test, hourglass_um_crop_tiny.py:909)")
     p.add_argument("--data_source", type=str, default="auto", choices=["auto", "synthetic", "tfrecord"],
                    help="tfrecord = the reference's shards under --data_dir; auto = tfrecord when every shard exists, else synthetic")
     p.add_argument("--data_dir", type=str, default=None, help="dataset root (default: the reference's ./exp/data/<dataset>/)")
@@ -172,22 +174,36 @@ class JointDetectionModel:
         """model.test: raw crops -> xyz mm (B,3J)."""
         return self.engine.infer(dms, cfgs, coms, out=out)
 
-    # ---- checkpoint: flat fp32 buffers in the reference's directory layout (SURVEY.md section 5) --------------
-    def save(self, step):
+    # ---- checkpoints (SURVEY.md section 5, 8f-4) ----------------------------------------------------------------
+    # `model.ckpt-<step>.{index,data-00000-of-00001}` is the reference's own format (tf.train.Saver V2 bundle with the um_v1
+    # variable names, densereg_b200/tf_checkpoint.py): what train() of the reference writes, what the authors' pretrained
+    # models ship as, and what restore() reads here.  save() writes it too, next to a flat `.pt` of the same buffers.
+    def save(self, step, tf_bundle=True):
         os.makedirs(self.train_dir, exist_ok=True)
         path = os.path.join(self.train_dir, "model.ckpt-%d.pt" % step)
         e = self.engine
         torch.save(dict(step=step, params=e.params.cpu(), state=e.state.cpu(), adam_m=e.adam_m.cpu(), adam_v=e.adam_v.cpu(),
                         config=dict(num_stack=e.S, num_fea=e.F, num_jnt=e.J)), path)
+        if tf_bundle:
+            tf_checkpoint.export_checkpoint(e, os.path.join(self.train_dir, "model.ckpt-%d" % step), global_step=step)
         return path
 
     def restore(self, step):
-        ck = torch.load(os.path.join(self.train_dir, "model.ckpt-%d.pt" % step), map_location="cpu")
+        """saver.restore(sess, train_dir/model.ckpt-<step>) (test_model.py:31-35; the reference tests with step -1)."""
+        prefix = os.path.join(self.train_dir, "model.ckpt-%d" % step)
         e = self.engine
+        if os.path.exists(prefix + ".index"):
+            got = tf_checkpoint.import_checkpoint(e, prefix)
+            return got if got else step
+        ck = torch.load(prefix + ".pt", map_location="cpu")
         e.load_flat(ck["params"], ck["state"])
         if e.adam_m is not None:
             e.adam_m.copy_(ck["adam_m"]); e.adam_v.copy_(ck["adam_v"])
         return ck["step"]
+
+    def has_checkpoint(self, step):
+        prefix = os.path.join(self.train_dir, "model.ckpt-%d" % step)
+        return os.path.exists(prefix + ".index") or os.path.exists(prefix + ".pt")
 
 
 def augment(engine, tens, rng):
@@ -214,7 +230,7 @@ def allreduce_gradients(grads, world):
     return grads
 
 
-def train(model, rank=0, world=1, log=print):
+def train(model, rank=0, world=1, log=print, start_step=0):
     """model/train_single_gpu.py:37-177 (loop :138-175) with per-rank sharding of each micro-batch.  Writes the reference's
     `training_log.txt` (:135-158) and `validation_log.txt` (hourglass_um_crop_tiny.py:126,816-840) under train_dir."""
     f = model.flags
@@ -229,7 +245,7 @@ def train(model, rank=0, world=1, log=print):
         os.makedirs(model.train_dir, exist_ok=True)
         tlog = open(os.path.join(model.train_dir, "training_log.txt"), "a")
         vlog = open(os.path.join(model.train_dir, "validation_log.txt"), "a")
-    for step in range(max_steps):
+    for step in range(start_step, max_steps):                                      # resume: train_single_gpu.py:125-128
         eng.zero_grads()                                                           # reset_op :139
         for sub in range(f.sub_batch):                                             # :140-148
             tens = list(model.train_dataset.batch_device(eng, f.batch_size, seed=step * f.sub_batch + sub, lo=lo, hi=hi)[:4])
@@ -315,8 +331,17 @@ def main(argv=None):
     ds, val = open_datasets(flags)
     model = JointDetectionModel(ds, flags, val_dataset=val, device=local, world=world)
     model.engine.init_params(seed=0)
+    step = flags.restore_step if flags.restore_step is not None else (None if flags.is_train else -1)
+    start_step = 0
+    if step is not None and model.has_checkpoint(step):
+        start_step = model.restore(step)
+        print("[densereg_b200] restored %s/model.ckpt-%d" % (model.train_dir, step))
+    elif flags.restore_step is not None:
+        raise FileNotFoundError("no checkpoint %s/model.ckpt-%d(.index|.pt)" % (model.train_dir, step))
+    elif not flags.is_train:
+        print("[densereg_b200] no checkpoint %s/model.ckpt--1 -- testing the freshly initialised network" % model.train_dir)
     if flags.is_train:
-        train(model, rank, world)
+        train(model, rank, world, start_step=max(start_step, 0))
     else:
         test(model)
     if world > 1:

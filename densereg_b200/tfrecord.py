@@ -32,12 +32,59 @@ def _crc_table():
     return _CRC_TABLE
 
 
-def crc32c(data):
+def _crc_scalar(buf, c):
     tab = _crc_table()
-    c = 0xFFFFFFFF
-    for b in bytes(data):
+    for b in buf:
         c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    return c
+
+
+_LANE = 1024          # bytes per lane of the vectorised path
+_SHIFT_TABS = None    # 4 x 256 tables of the linear map "advance the CRC register over _LANE zero bytes"
+
+
+def _shift_tables():
+    """The CRC register update is linear over GF(2): crc(A||B) = shift_{|B|}(crc(A)) xor crc0(B).  Build shift_{_LANE} by
+    squaring the one-byte step (as columns = images of the 32 unit vectors), then expand it to byte-indexed tables."""
+    global _SHIFT_TABS
+    if _SHIFT_TABS is None:
+        tab = _crc_table()
+        cols = [tab[(1 << i) & 0xFF] ^ ((1 << i) >> 8) for i in range(32)]       # one zero byte
+        apply = lambda cs, v: _xor_all(cs[i] for i in range(32) if (v >> i) & 1)
+        n = _LANE
+        assert n & (n - 1) == 0
+        while n > 1:
+            cols = [apply(cols, c) for c in cols]
+            n >>= 1
+        _SHIFT_TABS = [[apply(cols, b << (8 * k)) for b in range(256)] for k in range(4)]
+    return _SHIFT_TABS
+
+
+def _xor_all(it):
+    r = 0
+    for v in it:
+        r ^= v
+    return r
+
+
+def crc32c(data):
+    """CRC-32C of a bytes-like object.  Long inputs are cut into _LANE-byte lanes whose CRCs advance together as one NumPy
+    vector (table look-ups over all lanes per byte position) and are then chained with the linear shift map."""
+    buf = memoryview(bytes(data))
+    n = len(buf)
+    lanes = n // _LANE
+    c = 0xFFFFFFFF
+    if lanes >= 8:
+        tab = np.array(_crc_table(), dtype=np.uint32)
+        a = np.frombuffer(buf[:lanes * _LANE], dtype=np.uint8).reshape(lanes, _LANE)
+        v = np.zeros(lanes, dtype=np.uint32)
+        for j in range(_LANE):
+            v = tab[(v ^ a[:, j]) & 0xFF] ^ (v >> 8)
+        t0, t1, t2, t3 = _shift_tables()
+        for x in v.tolist():
+            c = t0[c & 0xFF] ^ t1[(c >> 8) & 0xFF] ^ t2[(c >> 16) & 0xFF] ^ t3[c >> 24] ^ x
+        buf = buf[lanes * _LANE:]
+    return _crc_scalar(buf, c) ^ 0xFFFFFFFF
 
 
 def masked_crc32c(data):

@@ -19,6 +19,11 @@ def test_crc32c_known_answers():
     assert tfrecord.crc32c(bytes(32)) == 0x8A9136AA                         # RFC 3720 B.4: 32 bytes of zeros
     assert tfrecord.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43                # RFC 3720 B.4: 32 bytes of 0xFF
     assert tfrecord.crc32c(bytes(range(32))) == 0x46DD794E                  # RFC 3720 B.4: 0x00..0x1F
+    rng = np.random.RandomState(0)                                          # the lane-parallel path == the byte loop
+    for n in (8191, 8192, 8193, 70001):
+        d = rng.bytes(n)
+        assert tfrecord.crc32c(d) == tfrecord._crc_scalar(d, 0xFFFFFFFF) ^ 0xFFFFFFFF
+    assert tfrecord.crc32c(bytes(range(32)) * 1024) == tfrecord._crc_scalar(bytes(range(32)) * 1024, 0xFFFFFFFF) ^ 0xFFFFFFFF
     c = tfrecord.crc32c(b"abc")
     assert tfrecord.masked_crc32c(b"abc") == ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
 
