@@ -29,6 +29,7 @@ struct ConvProblem {
   const float* w_kmajor;   // tensor-core path: 16 B aligned K-major copy [tap][Cout][Cin] (hi part for 3xTF32), or null
   const float* w_kmajor_lo;// 3xTF32: lo part
   int wk_ld;               // row length (floats, multiple of 4) of the K-major copy: Cin rounded up to 4
+  int pair;                // 3xTF32 tensor-core path: allow the CTA-pair (cta_group::2) kernel for big layers (conv_tc_pair.cu)
   float* y; int y_cs;      // output view
   // epilogue: v = acc*scale[n] + shift[n]; relu; dropout; + res; + beta*y_old
   const float* scale;      // may be null (=1)
@@ -58,6 +59,9 @@ int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st);
 // tcgen05 path (conv_tc.cu). Returns 0 launches if the problem shape is not eligible.
 bool conv_tc_eligible(const ConvProblem& p);
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st);
+// CTA-pair (cta_group::2) 3xTF32 variant (conv_tc_pair.cu), opt-in (ConvProblem::pair); same contract as launch_conv_tc
+bool conv_tc_pair_wanted(const ConvProblem& p);
+int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st);
 bool wgrad_tc_eligible(const WgradProblem& p);
 int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st);
 

@@ -85,6 +85,7 @@ struct dr_handle {
   cudaStream_t wgrad_stream = nullptr;
   cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr}, ev_wdone[3] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool side_stream = true;
+  bool tc_pair = false;      // dr_config.reserved[1] != 0 or DENSEREG_TC_PAIR=1: CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers
   // inference CUDA graph (dr_config.reserved[0] != 0): the ~170 launches of dr_infer are captured once per (batch, pointers) key
   // on an internal stream and replayed with cudaGraphLaunch on the caller's stream -> B=1 latency is no longer launch-bound
   struct InferGraph { int B = 0; const void *dm = nullptr, *cfg = nullptr, *com = nullptr; void *xyz = nullptr, *top5 = nullptr;
@@ -368,7 +369,9 @@ struct Exec {
 
 int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
   if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) {
-    int n = launch_conv_tc(p, precision == DR_PREC_TF32X3, st);
+    ConvProblem q = p;
+    q.pair = p.pair ? p.pair : (h->tc_pair ? 1 : 0);
+    int n = launch_conv_tc(q, precision == DR_PREC_TF32X3, st);
     if (n > 0) { h->tc_launches += n; return n; }
   }
   return launch_conv_simt(p, st);
@@ -693,6 +696,7 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   dr_handle* h = new dr_handle();
   h->cfg = *cfg;
   h->precision = cfg->precision;
+  { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] != 0 || (env && env[0] == '1'); }
   Builder b{h, 0, 0, 0};
   b.build();
   *out = h;
@@ -925,7 +929,9 @@ int dr_data_aug(dr_handle* h, int B, int hw, int J, const float* dms, const floa
 }
 
 int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {
-  const bool reuse = (precision & 0x100) != 0 && h && h->wk; precision &= 0xff;
+  const bool reuse = (precision & 0x100) != 0 && h && h->wk;
+  const int force_pair = (precision & 0x200) != 0;          // debug: CTA-pair kernel for this call regardless of the handle's setting
+  precision &= 0xff;
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;
   if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
   const Layer& L = h->layers[layer];
@@ -933,7 +939,7 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
   if (precision != DR_PREC_FP32 && !reuse) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
-  set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout;
+  set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout; p.pair = force_pair ? 2 : 0;
   h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;

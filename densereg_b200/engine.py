@@ -24,7 +24,7 @@ def _ptr(t):
 
 class DenseRegEngine:
     def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="fp32", device=0,
-                 kernel_size=3, training=True, infer_graph=False):
+                 kernel_size=3, training=True, infer_graph=False, tc_pair=False):
         if not torch.cuda.is_available():
             raise DenseRegError("densereg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _ffi.load()
@@ -36,6 +36,7 @@ class DenseRegEngine:
                             precision=_ffi.PRECISIONS[precision] if isinstance(precision, str) else precision,
                             device=device)
         cfg.reserved[0] = 1 if infer_graph else 0          # dr_infer via a captured CUDA graph (same buffers every call)
+        cfg.reserved[1] = 1 if tc_pair else 0              # experimental: CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers
         self._h = C.c_void_p()
         torch.cuda.set_device(self.device)
         rc = self.lib.dr_create(C.byref(self._h), C.byref(cfg))
@@ -177,11 +178,11 @@ class DenseRegEngine:
     def optimizer_step(self, step, lr, accum_steps=1, world=1):
         self._check(self.lib.dr_optimizer_step(self._h, accum_steps, world, float(lr), int(step), self._stream()))
 
-    def debug_conv(self, layer, x, precision="fp32", reuse_weights=False, out=None):
+    def debug_conv(self, layer, x, precision="fp32", reuse_weights=False, out=None, pair=False):
         L = self._layers_cached()[layer]
         B = x.shape[0]
         y = out if out is not None else torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
-        self._check(self.lib.dr_debug_conv(self._h, layer, B, _ptr(x), _ptr(y), _ffi.PRECISIONS[precision] | (0x100 if reuse_weights else 0),
+        self._check(self.lib.dr_debug_conv(self._h, layer, B, _ptr(x), _ptr(y), _ffi.PRECISIONS[precision] | (0x100 if reuse_weights else 0) | (0x200 if pair else 0),
                                            self._stream()))
         return y
 
