@@ -126,12 +126,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp < 6) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
+    __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
     __shared__ int s_last;
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int et = q * 32 + lane;                        // 0..127 (warps 2..5 -> q = 2,3,0,1)
     const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    tc_epilogue_stage_affine(p, et, s_scale, s_shift);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
@@ -139,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
       tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, total_tiles, s_sum, s_sq, s_last,
-                       [&]() { mbar_arrive(&acc_empty[as]); });
+                       s_scale, s_shift, [&]() { mbar_arrive(&acc_empty[as]); });
     }
   } else if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
@@ -191,7 +193,7 @@ bool conv_tc_eligible(const ConvProblem& p) {
   if (p.Cin < 8 || (p.x_cs % 4) != 0 || (reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;   // only STRIDES must be 16 B multiples
   if (p.wk_ld < p.Cin || (p.wk_ld % 4) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.w_kmajor) & 15) != 0) return false;
-  if (p.Cout < 8) return false;
+  if (p.Cout < 8 || (p.Cout + 255) / 256 * 256 > TC_MAX_COUT) return false;     // shared-memory scale/shift tables
   if (p.pad_t != (p.k - 1) / 2 || p.pad_l != p.pad_t) return false;
   // tiny problems are latency-bound on the TMA/mbarrier pipeline (~18 us floor); below the threshold the FFMA kernel is used
   static double min_mmac = -1.0;
@@ -219,7 +221,14 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   t.tmem_cols = cols;
   t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;
   const int stage_bytes = (split3 ? 2 : 1) * (A_TILE_BYTES + BN * TC_BK * 4);
-  int stages = (208 * 1024) / stage_bytes;
+  // shared-memory budget: 227 KB per CTA minus the kernel's static part (statistics staging + scale/shift tables), barriers, alignment slack
+  static int smem_budget = 0;
+  if (!smem_budget) {
+    cudaFuncAttributes fa;
+    const size_t st_bytes = cudaFuncGetAttributes(&fa, conv_tc_kernel<true>) == cudaSuccess ? fa.sharedSizeBytes : 16 * 1024;
+    smem_budget = 227 * 1024 - (int)st_bytes - 2304;
+  }
+  int stages = smem_budget / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
@@ -253,10 +262,10 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   const int total_tiles = t.tiles_m * t.tiles_n;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (split3) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[1] = true; }
+    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304); attr_set[1] = true; }
     conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[0] = true; }
+    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304); attr_set[0] = true; }
     conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
   }
   return 1;

@@ -31,17 +31,37 @@ struct TcParams {
 
 using namespace tc;
 
+constexpr int TC_MAX_COUT = 768;     // capacity of the shared-memory scale/shift tables (largest Cout on the path: 515, dgrad of um_full1)
+
+// Per-channel epilogue constants, staged ONCE per kernel in shared memory by the 128 epilogue threads (named barrier 1): the tile
+// loop then reads them with broadcast LDS.128 instead of two dependent global loads per element.  Channels past Cout get scale 0 /
+// shift 0 (they are never stored).
+DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scale, float* s_shift) {
+  const int ncol = p.tiles_n * p.BN;
+  for (int c = et; c < ncol; c += 128) {
+    s_scale[c] = (c < p.Cout) ? (p.scale ? __ldg(p.scale + c) : 1.f) : 0.f;
+    s_shift[c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // Epilogue of ONE 128-row accumulator tile: TMEM -> registers -> (BRN statistics) -> scale/shift | bias, ReLU, dropout,
 // residual add, accumulate -> NHWC view; then the BRN finalize if this was the last tile of the layer.  Called by the four
 // epilogue warps (128 threads, named barrier 1).  tmem_acc = TMEM address of column 0 of this accumulator stage (lane 0);
 // release() is invoked by lane 0 of every warp once that warp's TMEM reads are complete (hands the stage back to the MMA issuer).
+// Every warp-uniform decision (scale? shift? relu? dropout? residual? accumulate? whole 32-column chunk inside Cout?) is taken ONCE per
+// 32-column chunk, and the residual / accumulate operands of a chunk are fetched as one batch of independent 16 B loads, so the chunk
+// is a straight line of independent instructions (the first version interleaved two dependent global loads and four branches per
+// element: 0.1 instructions per cycle per warp, 12 us per 128x128 tile -- profiles/r1_epilogue.md).
 template <class Release>
 DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0,
-                                int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, Release release) {
+                                int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, const float* s_scale,
+                                const float* s_shift, Release release) {
     const int m = tile_m * TC_BM + row;
     const bool mvalid = m < p.M;
     float* yr = p.y + (size_t)m * p.y_cs;
     const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
+    const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
     for (int cb = 0; cb < p.BN; cb += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
@@ -63,44 +83,68 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
         }
         s_sum[q][cb + lane] = a[0]; s_sq[q][cb + lane] = b2[0];
       }
-      if (!mvalid) continue;
+      const int nc = n0 + cb;                       // first channel of this chunk
+      if (!mvalid || nc >= p.Cout) continue;
+      float x[32];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int n = n0 + cb + g * 4;
-        if (n >= p.Cout) break;
-        float o[4];
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+      // ---- per-channel affine from the shared-memory tables (separate multiply and add, never contracted: same roundings as before)
+      if (has_scale) {
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + nc);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int nn = n + e;
-          float x = __uint_as_float(v[g * 4 + e]);
-          if (nn < p.Cout) {
-            if (p.scale) x = x * __ldg(p.scale + nn);
-            if (p.shift) x = x + __ldg(p.shift + nn);
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.dropout) x = dr_hash_keep(p.drop_seed, p.drop_tag, (uint64_t)m * p.Cout + nn) ? x * 2.0f : 0.f;
-          }
-          o[e] = x;
+        for (int g = 0; g < 8; ++g) {
+          const float4 c4 = sc4[g];
+          x[4 * g] = __fmul_rn(x[4 * g], c4.x); x[4 * g + 1] = __fmul_rn(x[4 * g + 1], c4.y);
+          x[4 * g + 2] = __fmul_rn(x[4 * g + 2], c4.z); x[4 * g + 3] = __fmul_rn(x[4 * g + 3], c4.w);
         }
-        if (vec_ok && n + 3 < p.Cout) {
-          if (rr) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rr + n);
-            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-          }
-          if (p.accumulate) {
-            const float4 y4 = *reinterpret_cast<const float4*>(yr + n);
-            o[0] += y4.x; o[1] += y4.y; o[2] += y4.z; o[3] += y4.w;
-          }
-          *reinterpret_cast<float4*>(yr + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
+      }
+      if (has_shift) {
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + nc);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int nn = n + e;
-            if (nn < p.Cout) {
-              float x = o[e];
-              if (rr) x += rr[nn];
-              if (p.accumulate) x += yr[nn];
-              yr[nn] = x;
-            }
+        for (int g = 0; g < 8; ++g) {
+          const float4 c4 = sh4[g];
+          x[4 * g] = __fadd_rn(x[4 * g], c4.x); x[4 * g + 1] = __fadd_rn(x[4 * g + 1], c4.y);
+          x[4 * g + 2] = __fadd_rn(x[4 * g + 2], c4.z); x[4 * g + 3] = __fadd_rn(x[4 * g + 3], c4.w);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+      }
+      if (p.dropout) {
+        const uint64_t base = (uint64_t)m * p.Cout + nc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = dr_hash_keep(p.drop_seed, p.drop_tag, base + i) ? x[i] * 2.0f : 0.f;
+      }
+      if (vec_ok && nc + 32 <= p.Cout) {
+        // ---- whole chunk inside Cout, 16 B aligned rows: batched 16 B loads, then 8 x 16 B stores
+        if (rr) {
+          float4 r4[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) r4[g] = *reinterpret_cast<const float4*>(rr + nc + 4 * g);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { x[4 * g] += r4[g].x; x[4 * g + 1] += r4[g].y; x[4 * g + 2] += r4[g].z; x[4 * g + 3] += r4[g].w; }
+        }
+        if (p.accumulate) {
+          float4 y4[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) y4[g] = *reinterpret_cast<const float4*>(yr + nc + 4 * g);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { x[4 * g] += y4[g].x; x[4 * g + 1] += y4[g].y; x[4 * g + 2] += y4[g].z; x[4 * g + 3] += y4[g].w; }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(yr + nc + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+      } else {
+        // ---- ragged chunk (channel tail, or rows that are not 16 B aligned): element by element
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int nn = nc + i;
+          if (nn < p.Cout) {
+            float o = x[i];
+            if (rr) o += rr[nn];
+            if (p.accumulate) o += yr[nn];
+            yr[nn] = o;
           }
         }
       }

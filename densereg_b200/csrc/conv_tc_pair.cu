@@ -12,8 +12,8 @@
 //   producer (warp 0)    waits its LOCAL empty[s], TMA-loads its own A tile (128 pixels x 32 ch) and its own half of the pre-split
 //                        weights (BN/2 couts x 32 ch, hi and lo) onto its LOCAL full[s]
 //   splitters (4 warps)  wait LOCAL full[s], rewrite A into hi/lo in place, fence.proxy.async, arrive on the LEADER's split[s]
-//                        (8 arrivals: 4 warps x 2 CTAs, release.cluster) -- this also tells the leader that the peer's B half landed
-//   MMA (leader, 1 thr)  waits split[s] (acquire.cluster), issues 12 x tcgen05.mma.cta_group::2 (M=256, N=BN, K=8: hi*lo, lo*hi, hi*hi),
+//                        (8 arrivals: 4 warps x 2 CTAs) -- this also tells the leader that the peer's B half landed
+//   MMA (leader, 1 thr)  waits split[s], issues 12 x tcgen05.mma.cta_group::2 (M=256, N=BN, K=8: hi*lo, lo*hi, hi*hi),
 //                        tcgen05.commit.cta_group::2 .multicast -> empty[s] of BOTH CTAs; after the last k-block -> acc_full[as] of both
 //   epilogue (4 warps)   each CTA drains its own 128 TMEM lanes (shared code: tc_epilogue_tile) and arrives on the LEADER's
 //                        acc_empty[as] (8 arrivals)
@@ -42,23 +42,11 @@ DR_DEVINL uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the DEFAULT semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id) does.  The data the
+// arrival publishes is this CTA's own shared memory, made visible to the tensor cores by fence.proxy.async; the arrival itself is only a
+// signal.  (A .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR per call -- measured: ~2400 cycles per k-block floor.)
 DR_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-DR_DEVINL void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-  } while (!ok);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 DR_DEVINL void tc_commit_pair(uint64_t* bar) {      // arrives on `bar` at the same offset in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -150,13 +138,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t it = 0, tcount = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters, ++tcount) {
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait_acq_cluster(&acc_empty[as], aph ^ 1);           // both epilogues have drained this accumulator stage
+        mbar_wait(&acc_empty[as], aph ^ 1);           // both epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait_acq_cluster(&split_bar[s], ph);
+          mbar_wait(&split_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t b_addr = a_addr + 2 * A_TILE_BYTES;
@@ -176,6 +164,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp < 6) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
+    __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
     __shared__ int s_last;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -184,6 +173,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
     const int total_cta_tiles = 2 * total_items;                  // every CTA tile (also the phantom one of an odd tail) counts once
+    tc_epilogue_stage_affine(p, et, s_scale, s_shift);
     uint32_t tcount = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters, ++tcount) {
       const int pair = item / p.tiles_n, n0 = (item - pair * p.tiles_n) * p.BN;
@@ -191,7 +181,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
       tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, pair * 2 + (int)rank, n0, total_cta_tiles, s_sum, s_sq,
-                       s_last, [&]() { mbar_arrive_cluster(acc_empty_leader + as * 8u); });
+                       s_last, s_scale, s_shift, [&]() { mbar_arrive_cluster(acc_empty_leader + as * 8u); });
     }
   } else {
     // ===================== A splitter (both CTAs): hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
@@ -259,7 +249,13 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   t.tmem_cols = cols;
   t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * (BN / 2) * TC_BK * 4;
-  int stages = (200 * 1024) / stage_bytes;
+  static int smem_budget = 0;
+  if (!smem_budget) {
+    cudaFuncAttributes fa;
+    const size_t st_bytes = cudaFuncGetAttributes(&fa, conv_tc_pair_kernel) == cudaSuccess ? fa.sharedSizeBytes : 16 * 1024;
+    smem_budget = 227 * 1024 - (int)st_bytes - 2304;
+  }
+  int stages = smem_budget / stage_bytes;
   if (stages > 6) stages = 6;
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
   if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
@@ -289,7 +285,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   const int items = ((t.tiles_m + 1) / 2) * t.tiles_n;
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304) != cudaSuccess) return 0;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));

@@ -367,22 +367,53 @@ struct Exec {
   View whole(int buf) const { View v; v.buf = buf; v.coff = 0; v.C = h->bufs[buf].C; return v; }
 };
 
+// DENSEREG_TRACE=1: every conv / wgrad launch is timed on its own (events + sync, so launches are serialised) and reported on stderr as
+//   TRACE <conv|dgrad|wgrad> B H Cin Cout k <kernel: tc|pair|simt> <ms>      -- the per-layer time table of a step (tools/layer_times.py)
+static bool trace_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DENSEREG_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+struct TraceScope {
+  cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t st; bool on;
+  explicit TraceScope(cudaStream_t s) : st(s), on(trace_on()) {
+    if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+  }
+  void done(const char* what, int B, int H, int Cin, int Cout, int k, const char* kern) {
+    if (!on) return;
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "TRACE %s %d %d %d %d %d %s %.4f\n", what, B, H, Cin, Cout, k, kern, ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+};
+
 int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
+  TraceScope tr(st);
   if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) {
     ConvProblem q = p;
     q.pair = p.pair ? p.pair : (h->tc_pair ? 1 : 0);
     int n = launch_conv_tc(q, precision == DR_PREC_TF32X3, st);
-    if (n > 0) { h->tc_launches += n; return n; }
+    if (n > 0) {
+      h->tc_launches += n;
+      tr.done(p.flip_taps ? "dgrad" : "conv", p.B, p.H, p.Cin, p.Cout, p.k, (precision == DR_PREC_TF32X3 && conv_tc_pair_wanted(q)) ? "pair" : "tc");
+      return n;
+    }
   }
-  return launch_conv_simt(p, st);
+  int n = launch_conv_simt(p, st);
+  tr.done(p.flip_taps ? "dgrad" : "conv", p.B, p.H, p.Cin, p.Cout, p.k, "simt");
+  return n;
 }
 
 int run_wgrad(dr_handle* h, const WgradProblem& p, int precision, cudaStream_t st) {
+  TraceScope tr(st);
   if (precision != DR_PREC_FP32 && wgrad_tc_eligible(p)) {
     int n = launch_wgrad_tc(p, precision == DR_PREC_TF32X3, st);
-    if (n > 0) { h->tc_launches += n; return n; }
+    if (n > 0) { h->tc_launches += n; tr.done("wgrad", p.B, p.H, p.Cin, p.Cout, p.k, "tc"); return n; }
   }
-  return launch_wgrad_simt(p, st);
+  int n = launch_wgrad_simt(p, st);
+  tr.done("wgrad", p.B, p.H, p.Cin, p.Cout, p.k, "simt");
+  return n;
 }
 
 // (re)build the aligned weight copies from the bound parameters; called once per forward pass
