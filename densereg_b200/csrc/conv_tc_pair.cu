@@ -19,7 +19,7 @@
 //                        acc_empty[as] (8 arrivals)
 // Accumulators are double-buffered in TMEM (2 x BN columns, allocated with cta_group::2 by warp 1 of both CTAs).
 //
-// STATUS: opt-in (dr_config.reserved[1] = 1 or DENSEREG_TC_PAIR=1); the default path is the one-CTA kernel.  See DESIGN.md section 4.1b.
+// Taken for Cout >= 128 and >= 64 work items (conv_tc_pair_wanted); off with dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0.  DESIGN.md 4.1b.
 #include "conv_tc_epilogue.cuh"
 #include <stdlib.h>
 

@@ -85,7 +85,7 @@ struct dr_handle {
   cudaStream_t wgrad_stream = nullptr;
   cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr}, ev_wdone[3] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool side_stream = true;
-  bool tc_pair = false;      // dr_config.reserved[1] != 0 or DENSEREG_TC_PAIR=1: CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers
+  bool tc_pair = true;       // CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers (dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0: off)
   // inference CUDA graph (dr_config.reserved[0] != 0): the ~170 launches of dr_infer are captured once per (batch, pointers) key
   // on an internal stream and replayed with cudaGraphLaunch on the caller's stream -> B=1 latency is no longer launch-bound
   struct InferGraph { int B = 0; const void *dm = nullptr, *cfg = nullptr, *com = nullptr; void *xyz = nullptr, *top5 = nullptr;
@@ -727,7 +727,8 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   dr_handle* h = new dr_handle();
   h->cfg = *cfg;
   h->precision = cfg->precision;
-  { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] != 0 || (env && env[0] == '1'); }
+  // CTA-pair (cta_group::2) 3xTF32 kernel for the big layers: on by default; dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0 turns it off
+  { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] >= 0 && !(env && env[0] == '0'); }
   Builder b{h, 0, 0, 0};
   b.build();
   *out = h;

@@ -24,7 +24,7 @@ def _ptr(t):
 
 class DenseRegEngine:
     def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="fp32", device=0,
-                 kernel_size=3, training=True, infer_graph=False, tc_pair=False):
+                 kernel_size=3, training=True, infer_graph=False, tc_pair=True):
         if not torch.cuda.is_available():
             raise DenseRegError("densereg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _ffi.load()
@@ -36,7 +36,7 @@ class DenseRegEngine:
                             precision=_ffi.PRECISIONS[precision] if isinstance(precision, str) else precision,
                             device=device)
         cfg.reserved[0] = 1 if infer_graph else 0          # dr_infer via a captured CUDA graph (same buffers every call)
-        cfg.reserved[1] = 1 if tc_pair else 0              # experimental: CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers
+        cfg.reserved[1] = 0 if tc_pair else -1             # CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers (default on)
         self._h = C.c_void_p()
         torch.cuda.set_device(self.device)
         rc = self.lib.dr_create(C.byref(self._h), C.byref(cfg))

@@ -57,7 +57,7 @@ typedef struct {
   int32_t precision;     /* dr_precision                 */
   int32_t device;        /* CUDA ordinal                 */
   int32_t reserved[7];   /* reserved[0] != 0: dr_infer replays a CUDA graph captured per (batch, pointer) key;
-                            reserved[1] != 0: 3xTF32 convs of the big layers run on CTA pairs (tcgen05 cta_group::2), experimental */
+                            reserved[1] < 0: do NOT run the 3xTF32 convs of the big layers on CTA pairs (tcgen05 cta_group::2; default on) */
 } dr_config;
 
 typedef struct dr_handle dr_handle;

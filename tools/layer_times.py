@@ -4,8 +4,8 @@ timed alone) and aggregates the TRACE lines by (kind, shape).  Usage: python too
 import collections, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 env = dict(os.environ, DENSEREG_TRACE="1", DENSEREG_SIDE_STREAM="0")
-if "--pair" in sys.argv:
-    env["DENSEREG_TC_PAIR"] = "1"
+if "--single" in sys.argv:
+    env["DENSEREG_TC_PAIR"] = "0"
 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_once.py"), "--micro", "2"], env=env, capture_output=True, text=True)
 rows = [l.split() for l in r.stderr.splitlines() if l.startswith("TRACE")]
 half = len(rows) // 2
