@@ -127,6 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue: TMEM -> registers -> global =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
     __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
+    __shared__ __align__(16) float s_stage[4][32 * TC_STAGE_LD];        // per-warp 32x32 transpose tile (coalesced epilogue)
     __shared__ int s_last;
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -141,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
       tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, total_tiles, s_sum, s_sq, s_last,
-                       s_scale, s_shift, [&]() { mbar_arrive(&acc_empty[as]); });
+                       s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
     }
   } else if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
@@ -226,7 +227,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   if (!smem_budget) {
     cudaFuncAttributes fa;
     const size_t st_bytes = cudaFuncGetAttributes(&fa, conv_tc_kernel<true>) == cudaSuccess ? fa.sharedSizeBytes : 16 * 1024;
-    smem_budget = 227 * 1024 - (int)st_bytes - 2304;
+    smem_budget = 227 * 1024 - (int)st_bytes - 1536;     // 1536 >= barriers + tmem slot + 1024 B alignment slack
   }
   int stages = smem_budget / stage_bytes;
   if (stages > 6) stages = 6;
@@ -238,6 +239,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   t.accumulate = p.accumulate; t.dropout = p.dropout; t.drop_seed = p.drop_seed; t.drop_tag = p.drop_tag;
   t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
   t.bn_update_state = p.bn_update_state;
+  { static int co = -1; if (co < 0) { const char* e = getenv("DENSEREG_TC_EPI_COALESCE"); co = (e && e[0] == '0') ? 0 : 1; } t.coalesce = co; }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
 
   // activation map: dims (C, W, H, B)
@@ -262,10 +264,10 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   const int total_tiles = t.tiles_m * t.tiles_n;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (split3) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304); attr_set[1] = true; }
+    if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[1] = true; }
     conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304); attr_set[0] = true; }
+    if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[0] = true; }
     conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
   }
   return 1;

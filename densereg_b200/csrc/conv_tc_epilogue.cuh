@@ -27,7 +27,9 @@ struct TcParams {
   const float* res; int res_cs; int accumulate;
   int dropout; unsigned long long drop_seed; unsigned int drop_tag;
   double* stats; unsigned int* stats_counter; const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
+  int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
 };
+constexpr int TC_STAGE_LD = 36;      // floats per staging row: 16 B aligned, conflict-free for float4 writes (row per lane) and row reads
 
 using namespace tc;
 
@@ -56,7 +58,7 @@ DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scal
 template <class Release>
 DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0,
                                 int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, const float* s_scale,
-                                const float* s_shift, Release release) {
+                                const float* s_shift, float* stg, Release release) {
     const int m = tile_m * TC_BM + row;
     const bool mvalid = m < p.M;
     float* yr = p.y + (size_t)m * p.y_cs;
@@ -84,7 +86,10 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
         s_sum[q][cb + lane] = a[0]; s_sq[q][cb + lane] = b2[0];
       }
       const int nc = n0 + cb;                       // first channel of this chunk
-      if (!mvalid || nc >= p.Cout) continue;
+      if (nc >= p.Cout) continue;
+      const bool chunk_vec = vec_ok && nc + 32 <= p.Cout;      // whole chunk inside Cout and 16 B aligned rows (warp-uniform)
+      const bool transposed = chunk_vec && p.coalesce;
+      if (!transposed && !mvalid) continue;
       float x[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
@@ -116,7 +121,44 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = dr_hash_keep(p.drop_seed, p.drop_tag, base + i) ? x[i] * 2.0f : 0.f;
       }
-      if (vec_ok && nc + 32 <= p.Cout) {
+      if (transposed) {
+        // ---- lane = row  ->  (8 lanes per row) x (4 rows per instruction): every global access of the warp is 4 whole 128 B row segments
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(stg + lane * TC_STAGE_LD + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+        __syncwarp();
+        const int rsub = lane >> 3, cc = (lane & 7) * 4;
+        const int mrow0 = tile_m * TC_BM + q * 32 + rsub;
+        float4 o4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o4[j] = *reinterpret_cast<const float4*>(stg + (4 * j + rsub) * TC_STAGE_LD + cc);
+        if (p.res) {
+          float4 r4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int mr = mrow0 + 4 * j;
+            r4[j] = mr < p.M ? *reinterpret_cast<const float4*>(p.res + (size_t)mr * p.res_cs + nc + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o4[j].x += r4[j].x; o4[j].y += r4[j].y; o4[j].z += r4[j].z; o4[j].w += r4[j].w; }
+        }
+        if (p.accumulate) {
+          float4 y4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int mr = mrow0 + 4 * j;
+            y4[j] = mr < p.M ? *reinterpret_cast<const float4*>(p.y + (size_t)mr * p.y_cs + nc + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o4[j].x += y4[j].x; o4[j].y += y4[j].y; o4[j].z += y4[j].z; o4[j].w += y4[j].w; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int mr = mrow0 + 4 * j;
+          if (mr < p.M) *reinterpret_cast<float4*>(p.y + (size_t)mr * p.y_cs + nc + cc) = o4[j];
+        }
+        __syncwarp();                               // the staging tile is rewritten by the next chunk
+      } else if (chunk_vec) {
         // ---- whole chunk inside Cout, 16 B aligned rows: batched 16 B loads, then 8 x 16 B stores
         if (rr) {
           float4 r4[8];

@@ -165,6 +165,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
     __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
+    __shared__ __align__(16) float s_stage[4][32 * TC_STAGE_LD];        // per-warp 32x32 transpose tile (coalesced epilogue)
     __shared__ int s_last;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -181,7 +182,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
       tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, pair * 2 + (int)rank, n0, total_cta_tiles, s_sum, s_sq,
-                       s_last, s_scale, s_shift, [&]() { mbar_arrive_cluster(acc_empty_leader + as * 8u); });
+                       s_last, s_scale, s_shift, s_stage[q], [&]() { mbar_arrive_cluster(acc_empty_leader + as * 8u); });
     }
   } else {
     // ===================== A splitter (both CTAs): hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
@@ -233,7 +234,12 @@ bool conv_tc_pair_wanted(const ConvProblem& p) {
   const int M = p.B * p.H * p.W;
   int BN = (p.Cout + 15) / 16 * 16; if (BN > 256) BN = 256;
   const int items = ((M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((p.Cout + BN - 1) / BN);
-  return items >= 64;
+  // only main-loop-bound layers gain from the shared B tile; short reductions are epilogue-bound and run better as 128-pixel tiles
+  // (finer work items, less tail idling): measured 17-18 us per 256x256 item vs 8 us per 128x128 tile at <= 8 k-blocks
+  static int min_work = -1;
+  if (min_work < 0) { const char* e = getenv("DENSEREG_TC_PAIR_MINWORK"); min_work = e ? atoi(e) : 4096; }
+  const int num_kb = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
+  return items >= 64 && num_kb * BN >= min_work;
 }
 
 // Same contract as launch_conv_tc (conv_tc.cu) with split3 = 1; the caller has checked conv_tc_eligible(p).
@@ -253,7 +259,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   if (!smem_budget) {
     cudaFuncAttributes fa;
     const size_t st_bytes = cudaFuncGetAttributes(&fa, conv_tc_pair_kernel) == cudaSuccess ? fa.sharedSizeBytes : 16 * 1024;
-    smem_budget = 227 * 1024 - (int)st_bytes - 2304;
+    smem_budget = 227 * 1024 - (int)st_bytes - 1536;     // 1536 >= barriers + tmem slot + 1024 B alignment slack
   }
   int stages = smem_budget / stage_bytes;
   if (stages > 6) stages = 6;
@@ -264,6 +270,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   t.accumulate = p.accumulate; t.dropout = p.dropout; t.drop_seed = p.drop_seed; t.drop_tag = p.drop_tag;
   t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
   t.bn_update_state = p.bn_update_state;
+  { static int co = -1; if (co < 0) { const char* e = getenv("DENSEREG_TC_EPI_COALESCE"); co = (e && e[0] == '0') ? 0 : 1; } t.coalesce = co; }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;
 
   CUtensorMap ma, mw, mwlo;
@@ -285,7 +292,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   const int items = ((t.tiles_m + 1) / 2) * t.tiles_n;
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 2304) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
