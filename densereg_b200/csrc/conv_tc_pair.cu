@@ -234,10 +234,10 @@ bool conv_tc_pair_wanted(const ConvProblem& p) {
   const int M = p.B * p.H * p.W;
   int BN = (p.Cout + 15) / 16 * 16; if (BN > 256) BN = 256;
   const int items = ((M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((p.Cout + BN - 1) / BN);
-  // only main-loop-bound layers gain from the shared B tile; short reductions are epilogue-bound and run better as 128-pixel tiles
-  // (finer work items, less tail idling): measured 17-18 us per 256x256 item vs 8 us per 128x128 tile at <= 8 k-blocks
+  // DENSEREG_TC_PAIR_MINWORK (k-blocks x BN) can keep short reductions on the one-CTA kernel; measured on the whole training step
+  // (B=40): threshold 0 -> 1845 crops/s, 4096 -> 1837, 8192 -> 1797, so every Cout >= 128 layer with enough work items takes the pair kernel
   static int min_work = -1;
-  if (min_work < 0) { const char* e = getenv("DENSEREG_TC_PAIR_MINWORK"); min_work = e ? atoi(e) : 4096; }
+  if (min_work < 0) { const char* e = getenv("DENSEREG_TC_PAIR_MINWORK"); min_work = e ? atoi(e) : 0; }
   const int num_kb = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
   return items >= 64 && num_kb * BN >= min_work;
 }
