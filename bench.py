@@ -25,9 +25,9 @@ sys.path.insert(0, ROOT)
 TRAIN_GFLOP_PER_CROP = {16: 29.37, 14: 29.19, 21: 29.82}
 METRIC = "depth-crops/sec (128x128, 2-stack fea=128) training step"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (conv on s0/um_comb/c2, B=40), from the
-# `ncu --set full` captures summarised in profiles/r1_tensor_core_path.md (algorithmic: 42 MB in + 42 MB out + 2.4 MB weights;
-# the output is still L2-resident when the capture ends)
-NCU_TRAFFIC_BYTES = {"tf32x3": 48.5e6, "tf32": 47.4e6, "fp32": 51.0e6}
+# `ncu --set full` captures summarised in profiles/r1_final.md (tf32x3 = the CTA-pair kernel: 46.8 MB read + 4.3 MB written) and
+# profiles/r1_tensor_core_path.md (algorithmic: 42 MB in + 42 MB out + 2.4 MB weights; the output is still L2-resident when the capture ends)
+NCU_TRAFFIC_BYTES = {"tf32x3": 51.1e6, "tf32": 47.4e6, "fp32": 51.0e6}
 
 
 def measured_peaks():
@@ -311,7 +311,8 @@ def main():
     step_tflops = value / world * TRAIN_GFLOP_PER_CROP[J] / 1e3
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_burst"], "traffic": NCU_TRAFFIC_BYTES.get(args.precision),
-                "kernel": "conv implicit-GEMM (%s path) on s0/um_comb/c2 3x3 256->256, B=%d" % (args.precision, B),
+                "kernel": "conv implicit-GEMM (%s path%s) on s0/um_comb/c2 3x3 256->256, B=%d"
+                          % (args.precision, ", tcgen05 cta_group::2 CTA pairs" if args.precision == "tf32x3" and os.environ.get("DENSEREG_TC_PAIR", "1") != "0" else "", B),
                 "kernel_ms": k_ms, "peak_source": peaks["src"] + " dense bf16 cuBLAS burst (tf32 kind nominally half)",
                 "whole_step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"], "frac": step_tflops / peaks["bf16_sustained"],
                                "note": "29.37 GFLOP/crop (fwd+dgrad+wgrad conv FLOPs) x crops/s per GPU vs sustained measured peak"}}
