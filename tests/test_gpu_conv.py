@@ -99,3 +99,47 @@ def test_conv_tensor_core_path(setup, precision, tol, B):
     bad = {k: v for k, v in rep.items() if max(v["fwd"], v["dgrad"], v["wgrad"]) > tol}
     assert not bad, bad
     assert sum(v["tc_launches"] for v in rep.values()) >= len(TC_LAYERS), "tensor-core path was not taken"
+
+
+PAIR_CASES = [("s0/um_comb/c2", 40), ("s0/um_full2", 40), ("s0/um_res2/c2", 40), ("s0/um_res1/skip", 40), ("s0/um_comb/c3", 3), ("s0/um_out", 7),
+              ("s0/hg/n2/lower3/c1", 5), ("s0/hg/n3/upper1/c2", 3)]
+
+
+def test_pair_kernel_bit_identical_to_one_cta_kernel(built_lib):
+    """conv_tc_pair_kernel (tcgen05 cta_group::2, 256-pixel tiles) must reproduce conv_tc_kernel bit for bit: same k order, same three
+    products per k-step, same epilogue.  Covers big layers at the bench batch, odd tile counts (phantom peer tile), tiles that span
+    several images (4x4 maps), ragged Cin (160) and a narrow Cout (48).  The one-CTA kernel itself is pinned to the oracle above."""
+    from densereg_b200.engine import DenseRegEngine
+    eng = DenseRegEngine(2, 128, 16, max_batch=40, precision="tf32x3", training=False, tc_pair=False)
+    eng.init_params(0, 0.05)
+    L = eng.layers(); names = [l["name"] for l in L]
+    for name, B in PAIR_CASES:
+        li = names.index(name); l = L[li]
+        g = torch.Generator(device="cuda").manual_seed(li)
+        x = torch.randn(B, l["in_hw"], l["in_hw"], l["cin"], device="cuda", generator=g)
+        y0 = eng.debug_conv(li, x, "tf32x3")                                   # handle has the pair path off -> one-CTA kernel
+        y1 = eng.debug_conv(li, x, "tf32x3", reuse_weights=True, pair=True)    # forced CTA-pair kernel
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(y1).all()), name
+        assert torch.equal(y0, y1), "%s B=%d: max |diff| %.3e" % (name, B, float((y0 - y1).abs().max()))
+
+
+def test_pair_default_training_step_matches_one_cta(built_lib):
+    """Whole micro-batch (B=40 so that the big layers take the pair kernel) with the pair path on (default) vs off: same loss, gradients equal up
+    to the order of the fp32 atomics in wgrad / BRN statistics."""
+    from densereg_b200.engine import DenseRegEngine
+    from densereg_b200 import synth
+    B, J = 40, 16
+    d, po, cf, co = [torch.from_numpy(a).cuda() for a in synth.make_batch(B, J, seed=0)]
+    out = {}
+    for pair in (False, True):
+        eng = DenseRegEngine(2, 128, J, max_batch=B, precision="tf32x3", training=True, tc_pair=pair)
+        eng.init_params(0)
+        eng.zero_grads()
+        loss = eng.loss_backward(d, po, cf, co, dropout_seed=1).clone()
+        torch.cuda.synchronize()
+        out[pair] = (loss.cpu(), eng.grads.clone().cpu())
+        eng.close(); del eng
+    la, ga = out[False]; lb, gb = out[True]
+    assert float(((la - lb).abs() / la.abs().clamp_min(1e-30)).max()) < 1e-6
+    assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())

@@ -116,3 +116,20 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "crops/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_dataset_switch_and_checkpoint_flags(tmp_path):
+    """open_datasets: synthetic unless the reference's TFRecord shards exist (hourglass_um_crop_tiny.py:886-906); --restore_step / --data_* flags parse."""
+    from densereg_b200 import model as M
+    flags = M.build_argparser().parse_args(["--dataset", "icvl", "--is_train", "False", "--data_dir", str(tmp_path / "nope")])
+    assert flags.data_source == "auto" and flags.restore_step is None
+    logs = []
+    ds, val = M.open_datasets(flags, log=logs.append)
+    assert isinstance(ds, M.SyntheticDataset) and ds.subset == "testing" and val.jnt_num == 16 and "synthetic" in logs[-1]
+    flags.data_source = "tfrecord"
+    with pytest.raises(FileNotFoundError):
+        M.open_datasets(flags, log=logs.append)
+    flags.data_source = "synthetic"
+    assert isinstance(M.open_datasets(flags, log=logs.append)[0], M.SyntheticDataset)
+    f2 = M.build_argparser().parse_args(["--restore_step", "-1", "--dataset", "msra", "--pid", "3"])
+    assert f2.restore_step == -1 and f2.pid == 3
