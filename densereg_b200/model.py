@@ -66,8 +66,10 @@ class SyntheticDataset:
     }
 
     def __init__(self, name, subset, pid=0):
-        self.name, self.subset, self.pid = name, subset, pid
+        self.name, self.subset, self.pid = ("msra_P%d" % pid if name == "msra" else name), subset, pid    # msra.py:34
         self.jnt_num, self.approximate_num, self.exact_num = self._SPEC[name]
+        if name == "msra":
+            self.exact_num = datasets.MsraDataset.pid_num[pid]                     # msra.py:66-73
         self._cursor = 0
 
     def batch(self, batch_size, seed):
@@ -306,18 +308,19 @@ def test(model, out_path=None, log=print):
 
 
 def open_datasets(flags, log=print):
-    """The dataset switch of hourglass_um_crop_tiny.py:886-906: (train_dataset, val_dataset)."""
-    subset = "training" if flags.is_train else "testing"
+    """The dataset switch of hourglass_um_crop_tiny.py:886-906: always (Dataset('training'), Dataset('testing')) -- the model / checkpoint
+    directory name comes from the TRAINING dataset also when testing (run_test, :873-884)."""
     if flags.data_source != "synthetic":
-        real = [datasets.open_dataset(flags.dataset, s, flags.pid, flags.data_dir) for s in (subset, "testing")]
-        if all(d.available() for d in real):
-            log("[densereg_b200] reading TFRecord shards from %s" % real[0].tf_dir)
+        real = [datasets.open_dataset(flags.dataset, s, flags.pid, flags.data_dir) for s in ("training", "testing")]
+        need = real if flags.is_train else real[1:]
+        if all(d.available() for d in need):
+            log("[densereg_b200] reading TFRecord shards from %s" % need[0].tf_dir)
             return real[0], real[1]
         if flags.data_source == "tfrecord":
-            missing = [p for d in real for p in d.filenames if not os.path.exists(p)]
+            missing = [p for d in need for p in d.filenames if not os.path.exists(p)]
             raise FileNotFoundError("TFRecord shards missing (first: %s)" % missing[0])
-        log("[densereg_b200] no TFRecord shards under %s -- using synthetic %s-shaped crops" % (real[0].tf_dir, flags.dataset))
-    return SyntheticDataset(flags.dataset, subset, flags.pid), SyntheticDataset(flags.dataset, "testing", flags.pid)
+        log("[densereg_b200] no TFRecord shards under %s -- using synthetic %s-shaped crops" % (need[0].tf_dir, flags.dataset))
+    return SyntheticDataset(flags.dataset, "training", flags.pid), SyntheticDataset(flags.dataset, "testing", flags.pid)
 
 
 def main(argv=None):

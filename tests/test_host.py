@@ -125,7 +125,7 @@ def test_dataset_switch_and_checkpoint_flags(tmp_path):
     assert flags.data_source == "auto" and flags.restore_step is None
     logs = []
     ds, val = M.open_datasets(flags, log=logs.append)
-    assert isinstance(ds, M.SyntheticDataset) and ds.subset == "testing" and val.jnt_num == 16 and "synthetic" in logs[-1]
+    assert isinstance(ds, M.SyntheticDataset) and ds.subset == "training" and val.subset == "testing" and val.jnt_num == 16 and "synthetic" in logs[-1]
     flags.data_source = "tfrecord"
     with pytest.raises(FileNotFoundError):
         M.open_datasets(flags, log=logs.append)
@@ -133,3 +133,5 @@ def test_dataset_switch_and_checkpoint_flags(tmp_path):
     assert isinstance(M.open_datasets(flags, log=logs.append)[0], M.SyntheticDataset)
     f2 = M.build_argparser().parse_args(["--restore_step", "-1", "--dataset", "msra", "--pid", "3"])
     assert f2.restore_step == -1 and f2.pid == 3
+    tr, te = M.open_datasets(f2, log=logs.append)
+    assert tr.name == "msra_P3" and tr.jnt_num == 21 and te.exact_num == 8488
