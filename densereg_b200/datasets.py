@@ -50,6 +50,15 @@ def _decode_image(data):
     return img[..., ::-1] if img.ndim == 3 else img                                  # BGR -> RGB
 
 
+def to_device(a, device):
+    """Host array -> tensor on `device`: pinned staging + asynchronous copy for CUDA devices, plain tensor otherwise (CPU tests of the drivers)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if getattr(device, "type", str(device)) == "cuda":
+        return t.pin_memory().to(device, non_blocking=True)
+    return t.to(device)
+
+
 class EndOfData(Exception):
     """tf.errors.OutOfRangeError of a one-epoch reader (test_model.py:64)."""
 
@@ -216,13 +225,12 @@ class BaseDataset(object):
     def batch_device(self, engine, batch_size, seed=0, lo=0, hi=None):
         """-> device tensors (dms (b,128,128,1), poses (b,3J), cfgs (b,6), coms (b,3)) and names; rows [lo,hi) of the global
         batch (the rank's shard, train_multi_gpu.py:63-64).  Training subsets shuffle forever, 'testing' is one ordered epoch."""
-        import torch
         if self._epoch_iter is None:
             train = self.subset != "testing"
             self._epoch_iter = self.examples(shuffle=train, seed=seed, epochs=None if train else 1)
         frames, poses, names, bbx = self.frame_batch(batch_size, self._epoch_iter, allow_partial=(self.subset == "testing"))
         hi = len(names) if hi is None else min(hi, len(names))
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory().to(engine.device, non_blocking=True)
+        up = lambda a: to_device(a[lo:hi], engine.device)
         f_d, p_d = up(frames), up(poses)
         dms, cfgs, coms = self.crop(engine, f_d, p_d, None if bbx is None else up(bbx))
         return dms, p_d, cfgs, coms, names[lo:hi]

@@ -82,7 +82,7 @@ class SyntheticDataset:
     def batch_device(self, engine, batch_size, seed=0, lo=0, hi=None):
         """Rows [lo,hi) of the global batch as device tensors (same contract as datasets.BaseDataset.batch_device)."""
         dms, poses, cfgs, coms, names = self.batch(batch_size, seed)
-        tens = [torch.from_numpy(a[lo:hi]).pin_memory().to(engine.device, non_blocking=True) for a in (dms, poses, cfgs, coms)]
+        tens = [datasets.to_device(a[lo:hi], engine.device) for a in (dms, poses, cfgs, coms)]
         return tens[0], tens[1], tens[2], tens[3], names[lo:hi]
 
 
