@@ -718,7 +718,11 @@ static bool brn_v4_shape(size_t npix, int C, unsigned* block, unsigned* grid) {
   const unsigned lanes = 256 / C4;
   *block = C4 * lanes;
   size_t g = (npix + (size_t)lanes * 8 - 1) / ((size_t)lanes * 8);
-  if (g > 148 * 8) g = 148 * 8;
+  // DENSEREG_BRN_BLOCKS: cap on the grid (default 148*8).  The reduce kernel ends with 2*C double atomics per BLOCK onto 2*C addresses, so a
+  // smaller cap trades memory-level parallelism for less atomic contention (profiles/r1_final.md section 4: to be tuned on the GPU).
+  static size_t cap = 0;
+  if (!cap) { const char* e = getenv("DENSEREG_BRN_BLOCKS"); const long v = e ? atol(e) : 0; cap = v > 0 ? (size_t)v : 148 * 8; }
+  if (g > cap) g = cap;
   if (g < 1) g = 1;
   *grid = (unsigned)g;
   return true;
