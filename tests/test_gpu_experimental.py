@@ -1,0 +1,24 @@
+"""Opt-in kernels that have NOT been measured / verified on a B200 yet (written at the end of round 1 when the GPU budget was spent):
+  DENSEREG_WGRAD_SWAP=2      wgrad with exchanged operand roles (M = cout, coalesced reductions)       wgrad_tc.cu
+  DENSEREG_WGRAD_PERSIST=1   persistent wgrad kernel with double-buffered TMEM accumulators            wgrad_tc.cu
+Each case re-runs the existing conv / network parity tests in a child process with the switch set (the switches are read once per
+process).  Skipped unless DENSEREG_TEST_EXPERIMENTAL=1, so that the default suite only covers what ships enabled."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DENSEREG_TEST_EXPERIMENTAL") != "1",
+                                                  reason="experimental kernels: set DENSEREG_TEST_EXPERIMENTAL=1")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_SWAP": "2"}, {"DENSEREG_WGRAD_SWAP": "1"}, {"DENSEREG_WGRAD_PERSIST": "1"},
+                                 {"DENSEREG_WGRAD_PERSIST": "1", "DENSEREG_WGRAD_SWAP": "1", "DENSEREG_WGRAD_WAVES": "4"}])
+def test_parity_suite_with_switch(env):
+    e = dict(os.environ, **env)
+    e.pop("DENSEREG_TEST_EXPERIMENTAL", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_conv.py", "tests/test_gpu_net.py", "-m", "gpu", "-x", "-q"], cwd=ROOT, env=e,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (env, r.stdout[-3000:])
