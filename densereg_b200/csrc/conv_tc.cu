@@ -144,6 +144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, total_tiles, s_sum, s_sq, s_last,
                        s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
     }
+    tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
   } else if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
     const int t = threadIdx.x - 192;                      // 0..SPLIT_THREADS-1
@@ -240,6 +241,8 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
   t.bn_update_state = p.bn_update_state;
   { static int co = -1; if (co < 0) { const char* e = getenv("DENSEREG_TC_EPI_COALESCE"); co = (e && e[0] == '0') ? 0 : 1; } t.coalesce = co; }
+  { static int pc = -1; if (pc < 0) { const char* e = getenv("DENSEREG_TC_STATS_PER_CTA"); pc = (e && e[0] == '1') ? 1 : 0; }
+    t.stats_per_cta = (pc && p.stats && !p.scale && !p.shift) ? 1 : 0; }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
 
   // activation map: dims (C, W, H, B)

@@ -27,6 +27,7 @@ struct TcParams {
   const float* res; int res_cs; int accumulate;
   int dropout; unsigned long long drop_seed; unsigned int drop_tag;
   double* stats; unsigned int* stats_counter; const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
+  int stats_per_cta;     // fused BRN statistics: accumulate per CTA in shared memory, ONE round of atomics + fence + counter per CTA (opt-in)
   int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
 };
 constexpr int TC_STAGE_LD = 36;      // floats per staging row: 16 B aligned, conflict-free for float4 writes (row per lane) and row reads
@@ -40,9 +41,13 @@ constexpr int TC_MAX_COUT = 768;     // capacity of the shared-memory scale/shif
 // shift 0 (they are never stored).
 DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scale, float* s_shift) {
   const int ncol = p.tiles_n * p.BN;
-  for (int c = et; c < ncol; c += 128) {
-    s_scale[c] = (c < p.Cout) ? (p.scale ? __ldg(p.scale + c) : 1.f) : 0.f;
-    s_shift[c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
+  if (p.stats && p.stats_per_cta) {      // raw output (no affine): the two tables serve as this CTA's running column sums / sums of squares
+    for (int c = et; c < ncol; c += 128) { s_scale[c] = 0.f; s_shift[c] = 0.f; }
+  } else {
+    for (int c = et; c < ncol; c += 128) {
+      s_scale[c] = (c < p.Cout) ? (p.scale ? __ldg(p.scale + c) : 1.f) : 0.f;
+      s_shift[c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
+    }
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
@@ -57,8 +62,8 @@ DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scal
 // element: 0.1 instructions per cycle per warp, 12 us per 128x128 tile -- profiles/r1_epilogue.md).
 template <class Release>
 DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0,
-                                int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, const float* s_scale,
-                                const float* s_shift, float* stg, Release release) {
+                                int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, float* s_scale,
+                                float* s_shift, float* stg, Release release) {
     const int m = tile_m * TC_BM + row;
     const bool mvalid = m < p.M;
     float* yr = p.y + (size_t)m * p.y_cs;
@@ -195,7 +200,18 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     tc_fence_before();
     __syncwarp();
     if (lane == 0) release();
-    if (p.stats) {
+    if (p.stats && p.stats_per_cta) {
+      // per-CTA accumulation: the tile's column sums go into the shared-memory running totals (tc_epilogue_finish publishes them once)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < p.BN; col += 128) {
+        const int n = n0 + col;
+        if (n < p.Cout) {
+          s_scale[n] += (s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col]);
+          s_shift[n] += (s_sq[0][col] + s_sq[1][col]) + (s_sq[2][col] + s_sq[3][col]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");                     // s_sum / s_sq are rewritten by the next tile
+    } else if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int col = et; col < p.BN; col += 128) {
         const int n = n0 + col;
@@ -213,6 +229,25 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
         brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
       }
     }
+}
+
+// After a CTA's last tile (per-CTA statistics mode only): publish the running totals with one round of double atomics, then the usual
+// "last arriver finalizes" protocol counted in CTAs instead of tiles.  Called by the 128 epilogue threads.
+DR_DEVINL void tc_epilogue_finish(const TcParams& p, int et, const float* acc_sum, const float* acc_sq, int& s_last) {
+  if (!(p.stats && p.stats_per_cta)) return;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int n = et; n < p.Cout; n += 128) {
+    const float a = acc_sum[n], b = acc_sq[n];
+    if (a != 0.f || b != 0.f) { atomicAdd(p.stats + n, (double)a); atomicAdd(p.stats + p.Cout + n, (double)b); }
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (et == 0) s_last = (atomicAdd(p.stats_counter, 1u) == gridDim.x - 1);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (s_last) {                                                         // last CTA of the layer: BRN finalize
+    __threadfence();
+    brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
+  }
 }
 
 }  // namespace tcconv
