@@ -141,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
-      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, total_tiles, s_sum, s_sq, s_last,
+      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
                        s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
@@ -243,6 +243,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   { static int co = -1; if (co < 0) { const char* e = getenv("DENSEREG_TC_EPI_COALESCE"); co = (e && e[0] == '0') ? 0 : 1; } t.coalesce = co; }
   { static int pc = -1; if (pc < 0) { const char* e = getenv("DENSEREG_TC_STATS_PER_CTA"); pc = (e && e[0] == '1') ? 1 : 0; }
     t.stats_per_cta = (pc && p.stats && !p.scale && !p.shift) ? 1 : 0; }
+  t.full_items = 0; t.tail_f = 1;
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;   // + 8.2 KB static (fused-stats staging)
 
   // activation map: dims (C, W, H, B)

@@ -27,6 +27,7 @@ struct TcParams {
   const float* res; int res_cs; int accumulate;
   int dropout; unsigned long long drop_seed; unsigned int drop_tag;
   double* stats; unsigned int* stats_counter; const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
+  int full_items, tail_f;  // pair kernel: items >= full_items are 1/tail_f-wide N slices of the last wave's items (tail_f = 1: off)
   int stats_per_cta;     // fused BRN statistics: accumulate per CTA in shared memory, ONE round of atomics + fence + counter per CTA (opt-in)
   int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
 };
@@ -61,7 +62,7 @@ DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scal
 // is a straight line of independent instructions (the first version interleaved two dependent global loads and four branches per
 // element: 0.1 instructions per cycle per warp, 12 us per 128x128 tile -- profiles/r1_epilogue.md).
 template <class Release>
-DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0,
+DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0, int bn,
                                 int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, float* s_scale,
                                 float* s_shift, float* stg, Release release) {
     const int m = tile_m * TC_BM + row;
@@ -69,7 +70,7 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     float* yr = p.y + (size_t)m * p.y_cs;
     const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
     const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
-    for (int cb = 0; cb < p.BN; cb += 32) {
+    for (int cb = 0; cb < bn; cb += 32) {          // bn = columns of this work item (p.BN, or a slice of it in the pair kernel's tail)
       uint32_t v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
       if (p.stats) {
@@ -203,7 +204,7 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     if (p.stats && p.stats_per_cta) {
       // per-CTA accumulation: the tile's column sums go into the shared-memory running totals (tc_epilogue_finish publishes them once)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int col = et; col < p.BN; col += 128) {
+      for (int col = et; col < bn; col += 128) {
         const int n = n0 + col;
         if (n < p.Cout) {
           s_scale[n] += (s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col]);
@@ -213,7 +214,7 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
       asm volatile("bar.sync 1, 128;" ::: "memory");                     // s_sum / s_sq are rewritten by the next tile
     } else if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int col = et; col < p.BN; col += 128) {
+      for (int col = et; col < bn; col += 128) {
         const int n = n0 + col;
         if (n < p.Cout) {
           atomicAdd(p.stats + n, (double)((s_sum[0][col] + s_sum[1][col]) + (s_sum[2][col] + s_sum[3][col])));

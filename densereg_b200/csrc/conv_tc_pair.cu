@@ -67,7 +67,8 @@ DR_DEVINL void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
 // Work item = (pixel-tile PAIR, n-tile); cluster c walks items c, c + #clusters, ...; CTA rank r owns pixel tile 2*pair + r.
 __global__ void __launch_bounds__(192 + SPLIT_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_wt,
+                    const __grid_constant__ CUtensorMap map_wlot, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bh_bytes = (p.BN / 2) * TC_BK * 4;                   // this CTA's half of one weight tile (hi or lo)
@@ -83,8 +84,23 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int pairs_m = (p.tiles_m + 1) >> 1;
-  const int total_items = pairs_m * p.tiles_n;
+  const int base_items = pairs_m * p.tiles_n;
+  // Tail splitting (p.tail_f > 1): the items of the last, partly filled wave (index >= p.full_items) are cut into tail_f slices along N so that
+  // they spread over all clusters instead of leaving most SMs idle for a whole item time (160 items on 74 clusters = 2.16 waves otherwise cost 3).
+  const int total_items = p.full_items + (base_items - p.full_items) * p.tail_f;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  struct PItem { int pair, n0, bn; };
+  auto decode = [&](int item) {
+    PItem w;
+    if (item < p.full_items) {
+      w.pair = item / p.tiles_n; w.n0 = (item - w.pair * p.tiles_n) * p.BN; w.bn = p.BN;
+    } else {
+      const int tq = item - p.full_items, whole = tq / p.tail_f, sub = tq - whole * p.tail_f, base = p.full_items + whole;
+      w.bn = p.BN / p.tail_f;
+      w.pair = base / p.tiles_n; w.n0 = (base - w.pair * p.tiles_n) * p.BN + sub * w.bn;
+    }
+    return w;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -106,14 +122,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(A_TILE_BYTES + 2 * bh_bytes);
       uint32_t it = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters) {
-        const int pair = item / p.tiles_n, n0 = (item - pair * p.tiles_n) * p.BN;
-        const int pix0 = (pair * 2 + (int)rank) * TC_BM;          // may lie past M for the odd tail: TMA zero-fills, the epilogue masks
+        const PItem w = decode(item);
+        const bool sliced = w.bn != p.BN;
+        const uint32_t tx = (uint32_t)(A_TILE_BYTES + 2 * (w.bn / 2) * TC_BK * 4);
+        const int pix0 = (w.pair * 2 + (int)rank) * TC_BM;        // may lie past M for the odd tail: TMA zero-fills, the epilogue masks
         const int img = pix0 / (p.H * p.W);
         const int y0 = (pix0 - img * p.H * p.W) / p.W;
-        const int nb0 = n0 + (int)rank * (p.BN / 2);              // this CTA's half of the cout tile
+        const int nb0 = w.n0 + (int)rank * (w.bn / 2);            // this CTA's half of the cout tile (slice)
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -126,17 +143,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tma_load_4d(&map_a, &full_bar[s], st, c0, dx, y0 + dy, img);
           uint8_t* bdst = st + 2 * A_TILE_BYTES;
           const int wtap = p.flip_taps ? p.ksz * p.ksz - 1 - tap : tap;
-          tma_load_3d(&map_w, &full_bar[s], bdst, c0, nb0, wtap);
-          tma_load_3d(&map_wlo, &full_bar[s], bdst + bh_bytes, c0, nb0, wtap);
+          tma_load_3d(sliced ? &map_wt : &map_w, &full_bar[s], bdst, c0, nb0, wtap);                   // lo stays at the full-size offset
+          tma_load_3d(sliced ? &map_wlot : &map_wlo, &full_bar[s], bdst + bh_bytes, c0, nb0, wtap);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters, ++tcount) {
+        const PItem w = decode(item);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(w.bn >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);           // both epilogues have drained this accumulator stage
         tc_fence_after();
@@ -177,11 +195,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_epilogue_stage_affine(p, et, s_scale, s_shift);
     uint32_t tcount = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters, ++tcount) {
-      const int pair = item / p.tiles_n, n0 = (item - pair * p.tiles_n) * p.BN;
+      const PItem w = decode(item);
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait_sleep(&acc_full[as], aph);
       tc_fence_after();
-      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, pair * 2 + (int)rank, n0, total_cta_tiles, s_sum, s_sq,
+      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, w.pair * 2 + (int)rank, w.n0, w.bn, total_cta_tiles, s_sum, s_sq,
                        s_last, s_scale, s_shift, s_stage[q], [&]() { mbar_arrive_cluster(acc_empty_leader + as * 8u); });
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
@@ -276,7 +294,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
     t.stats_per_cta = (pc && p.stats && !p.scale && !p.shift) ? 1 : 0; }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;
 
-  CUtensorMap ma, mw, mwlo;
+  CUtensorMap ma, mw, mwlo, mwt, mwlot;
   const int rows = TC_BM / p.W;
   const int bh = rows < p.H ? rows : p.H;
   const int bb = rows < p.H ? 1 : rows / p.H;
@@ -294,6 +312,22 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
   const int items = ((t.tiles_m + 1) / 2) * t.tiles_n;
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
+  // tail splitting (opt-in, DENSEREG_TC_PAIR_TAIL=1): slice the last wave's r items by the largest power of two f with f*r <= clusters
+  t.full_items = items; t.tail_f = 1;
+  mwt = mw; mwlot = mwlo;
+  {
+    static int tail = -1;
+    if (tail < 0) { const char* e = getenv("DENSEREG_TC_PAIR_TAIL"); tail = (e && e[0] == '1') ? 1 : 0; }
+    const int r = items % clusters;
+    if (tail && items > clusters && r > 0 && 2 * r <= clusters) {
+      int f = 2;
+      while (2 * f * r <= clusters && f < 8 && (BN / (2 * f)) % 16 == 0 && BN / (2 * f) >= 32) f *= 2;
+      if ((BN / f) % 16 == 0 && BN / f >= 32) {
+        cuuint32_t wbt[3] = {(cuuint32_t)TC_BK, (cuuint32_t)(BN / f / 2), 1};
+        if (tc::encode_map(&mwt, p.w_kmajor, 3, wd, ws, wbt) && tc::encode_map(&mwlot, p.w_kmajor_lo, 3, wd, ws, wbt)) { t.tail_f = f; t.full_items = items - r; }
+      }
+    }
+  }
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
@@ -304,6 +338,6 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, t) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, mwt, mwlot, t) != cudaSuccess) { cudaGetLastError(); return 0; }
   return 1;
 }
