@@ -16,6 +16,7 @@ run base DENSEREG_NOP=1
 run brn_blocks_296 DENSEREG_BRN_BLOCKS=296
 run brn_blocks_592 DENSEREG_BRN_BLOCKS=592
 run stats_per_cta DENSEREG_TC_STATS_PER_CTA=1
+run pool_bwd_v4 DENSEREG_POOL_BWD_V4=1
 run pair_tail DENSEREG_TC_PAIR_TAIL=1
 run wgrad_swap DENSEREG_WGRAD_SWAP=1
 run wgrad_persist DENSEREG_WGRAD_PERSIST=1
