@@ -763,17 +763,20 @@ int launch_brn_bwd_fused(size_t npix, int C, const float* dy, int dy_cs, const f
   }
   return 1;
 }
-// block / grid of the channel-stationary float4 kernels: blockDim = C4 * floor(256 / C4); every thread gets >= 8 pixels when there are enough
-static bool brn_v4_shape(size_t npix, int C, unsigned* block, unsigned* grid) {
+// block / grid of the channel-stationary float4 kernels: blockDim = C4 * floor(256 / C4); every thread gets >= 8 pixels when there are enough.
+// `cap` bounds the grid.  The reduce kernel ends with 2*C double atomics per BLOCK onto 2*C addresses (64 lines at C = 512), so its time grows
+// with the block count once the atomics serialise: 1184 blocks x 16 atomics per line = 19 k atomics per line ~ 20 us per launch, twice the
+// streaming time (profiles/r1_final.md section 4) -> 2 blocks per SM for the reduce (still > 9 MB of loads in flight), 8 per SM for the apply.
+// DENSEREG_BRN_BLOCKS overrides both.
+static bool brn_v4_shape(size_t npix, int C, unsigned* block, unsigned* grid, size_t cap) {
   const unsigned C4 = (unsigned)C / 4;
   if (C % 4 != 0 || C4 == 0 || C4 > 256 || npix >= 0x7FFFFFFFull) return false;
   const unsigned lanes = 256 / C4;
   *block = C4 * lanes;
   size_t g = (npix + (size_t)lanes * 8 - 1) / ((size_t)lanes * 8);
-  // DENSEREG_BRN_BLOCKS: cap on the grid (default 148*8).  The reduce kernel ends with 2*C double atomics per BLOCK onto 2*C addresses, so a
-  // smaller cap trades memory-level parallelism for less atomic contention (profiles/r1_final.md section 4: to be tuned on the GPU).
-  static size_t cap = 0;
-  if (!cap) { const char* e = getenv("DENSEREG_BRN_BLOCKS"); const long v = e ? atol(e) : 0; cap = v > 0 ? (size_t)v : 148 * 8; }
+  static long env_cap = -1;
+  if (env_cap < 0) { const char* e = getenv("DENSEREG_BRN_BLOCKS"); env_cap = e ? atol(e) : 0; }
+  if (env_cap > 0) cap = (size_t)env_cap;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   *grid = (unsigned)g;
@@ -783,7 +786,7 @@ int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const 
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   unsigned block, grid;
-  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid)) {
+  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid, 148 * 2)) {
     brn_bwd_reduce_v4_kernel<<<grid, block, (size_t)block * 4 * 2 * sizeof(double), st>>>((unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4,
                                                                                         (const float4*)raw, raw_cs / 4, aff, bstat, relu, sums);
     return 1;
@@ -796,7 +799,7 @@ int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const f
                          const double* sums, float* draw, int draw_cs, float* gparam, cudaStream_t st) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   unsigned block, grid;
-  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && draw_cs % 4 == 0 && al(raw) && al(dy) && al(draw) && brn_v4_shape(npix, C, &block, &grid)) {
+  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && draw_cs % 4 == 0 && al(raw) && al(dy) && al(draw) && brn_v4_shape(npix, C, &block, &grid, 148 * 8)) {
     brn_bwd_apply_v4_kernel<<<grid, block, 0, st>>>((unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4, (const float4*)raw, raw_cs / 4, aff,
                                                     bstat, beta_gamma, relu, sums, (float4*)draw, draw_cs / 4, gparam);
   } else {

@@ -13,7 +13,7 @@ run() {
   env "$@" timeout -s KILL 120 python bench.py --no_cpu_baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('crops/s %.1f  ms/step %.2f  roofline kernel %.4f ms' % (d['value'], d['ms_per_step'], d['roofline']['kernel_ms']))" 2>&1 | tee -a $OUT
 }
 run base DENSEREG_NOP=1
-run brn_blocks_296 DENSEREG_BRN_BLOCKS=296
+run brn_blocks_1184 DENSEREG_BRN_BLOCKS=1184      # round-1 measured setting (reduce AND apply); default is now 296 for the reduce kernel only
 run brn_blocks_592 DENSEREG_BRN_BLOCKS=592
 run stats_per_cta DENSEREG_TC_STATS_PER_CTA=1
 run pool_bwd_v4 DENSEREG_POOL_BWD_V4=1
