@@ -60,6 +60,9 @@ int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st);
 bool conv_tc_eligible(const ConvProblem& p);
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st);
 // CTA-pair (cta_group::2) 3xTF32 variant (conv_tc_pair.cu), opt-in (ConvProblem::pair); same contract as launch_conv_tc
+// A-operand-in-tensor-memory 3xTF32 variant (conv_tc_atmem.cu), opt-in (DENSEREG_TC_A_TMEM); same contract
+int conv_tc_atmem_mode();
+int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st);
 bool conv_tc_pair_wanted(const ConvProblem& p);
 int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st);
 bool wgrad_tc_eligible(const WgradProblem& p);

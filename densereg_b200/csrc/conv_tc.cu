@@ -206,9 +206,17 @@ bool conv_tc_eligible(const ConvProblem& p) {
 
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
-  if (split3 && conv_tc_pair_wanted(p)) {                  // opt-in CTA-pair kernel for the big layers; falls through if its launch fails
-    const int n = launch_conv_tc_pair(p, st);
-    if (n > 0) return n;
+  if (split3) {
+    const bool pair_w = conv_tc_pair_wanted(p);
+    const int am = conv_tc_atmem_mode();                   // opt-in: split A operand in tensor memory (conv_tc_atmem.cu)
+    if (am == 2 || (am == 1 && !pair_w)) {
+      const int n = launch_conv_tc_atmem(p, st);
+      if (n > 0) return n;
+    }
+    if (pair_w) {                                          // CTA-pair kernel for the big layers; falls through if its launch fails
+      const int n = launch_conv_tc_pair(p, st);
+      if (n > 0) return n;
+    }
   }
   TcParams t;
   t.M = p.B * p.H * p.W; t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t; t.flip_taps = p.flip_taps;

@@ -3,6 +3,7 @@
   DENSEREG_WGRAD_PERSIST=1   persistent wgrad kernel with double-buffered TMEM accumulators            wgrad_tc.cu
   DENSEREG_TC_STATS_PER_CTA=1  fused BRN statistics accumulated per CTA (one fence + counter per CTA)   conv_tc_epilogue.cuh
   DENSEREG_TC_PAIR_TAIL=1    pair conv kernel: last wave's items sliced along N over all clusters         conv_tc_pair.cu
+  DENSEREG_TC_A_TMEM=1|2     3xTF32 conv with the split A operand in tensor memory (2: also instead of pairs)  conv_tc_atmem.cu
   DENSEREG_POOL_BWD_V4=1     float4-over-channels max-pool backward                                          ew.cu
   DENSEREG_BRN_BLOCKS=1184   the round-1 grid cap of the BRN-backward kernels (default now 296 for the reduce)   ew.cu
 Each case re-runs the existing conv / network parity tests in a child process with the switch set (the switches are read once per
@@ -20,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_SWAP": "2"}, {"DENSEREG_WGRAD_SWAP": "1"}, {"DENSEREG_WGRAD_PERSIST": "1"},
                                  {"DENSEREG_WGRAD_PERSIST": "1", "DENSEREG_WGRAD_SWAP": "1", "DENSEREG_WGRAD_WAVES": "4"},
-                                 {"DENSEREG_TC_STATS_PER_CTA": "1"}, {"DENSEREG_BRN_BLOCKS": "1184"}, {"DENSEREG_TC_PAIR_TAIL": "1"}, {"DENSEREG_POOL_BWD_V4": "1"}])
+                                 {"DENSEREG_TC_STATS_PER_CTA": "1"}, {"DENSEREG_BRN_BLOCKS": "1184"}, {"DENSEREG_TC_PAIR_TAIL": "1"}, {"DENSEREG_POOL_BWD_V4": "1"}, {"DENSEREG_TC_A_TMEM": "2"}, {"DENSEREG_TC_A_TMEM": "1"}])
 def test_parity_suite_with_switch(env):
     e = dict(os.environ, **env)
     e.pop("DENSEREG_TEST_EXPERIMENTAL", None)

@@ -16,6 +16,8 @@ run base DENSEREG_NOP=1
 run brn_blocks_1184 DENSEREG_BRN_BLOCKS=1184      # round-1 measured setting (reduce AND apply); default is now 296 for the reduce kernel only
 run brn_blocks_592 DENSEREG_BRN_BLOCKS=592
 run stats_per_cta DENSEREG_TC_STATS_PER_CTA=1
+run a_tmem_1 DENSEREG_TC_A_TMEM=1
+run a_tmem_2 DENSEREG_TC_A_TMEM=2
 run pool_bwd_v4 DENSEREG_POOL_BWD_V4=1
 run pair_tail DENSEREG_TC_PAIR_TAIL=1
 run wgrad_swap DENSEREG_WGRAD_SWAP=1
@@ -25,4 +27,6 @@ run wgrad_persist_swap_w4 DENSEREG_WGRAD_PERSIST=1 DENSEREG_WGRAD_SWAP=1 DENSERE
 timeout -s KILL 120 python tools/time_wgrad.py > gpurun_out/r2_wgrad_base.jsonl 2>&1
 DENSEREG_WGRAD_PERSIST=1 DENSEREG_WGRAD_SWAP=1 timeout -s KILL 120 python tools/time_wgrad.py > gpurun_out/r2_wgrad_persist_swap.jsonl 2>&1
 timeout -s KILL 90 python tools/layer_times.py > gpurun_out/r2_layer_times.txt 2>&1
+DENSEREG_TC_A_TMEM=2 timeout -s KILL 60 python tools/time_layers.py > gpurun_out/r2_eval_layers_atmem.jsonl 2>&1
+timeout -s KILL 60 python tools/time_layers.py > gpurun_out/r2_eval_layers_base.jsonl 2>&1
 echo done | tee -a $OUT
