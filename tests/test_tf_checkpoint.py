@@ -156,3 +156,26 @@ def test_gpu_engine_export_import_same_xyz(built_lib, tmp_path):
     dms, poses, cfgs, coms = synth.make_batch(2, 16, seed=0)
     cu = lambda x: torch.from_numpy(x).cuda()
     assert torch.equal(a.infer(cu(dms), cu(cfgs), cu(coms)), b.infer(cu(dms), cu(cfgs), cu(coms)))
+
+
+def test_golden_format_fixtures_are_stable(tmp_path):
+    """The committed byte fixtures (tests/golden/make_format_golden.py) still parse and the writers still reproduce them byte for byte."""
+    import importlib.util
+    from densereg_b200 import png, tfrecord
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_format_golden", os.path.join(gdir, "make_format_golden.py"))
+    G = importlib.util.module_from_spec(spec); spec.loader.exec_module(G)
+    recs = list(tfrecord.read_records(os.path.join(gdir, "tfrecord_2examples.bin"), verify="all"))
+    assert len(recs) == 2
+    for rec, (img, feat) in zip(recs, G.examples()):
+        assert rec == tfrecord.make_example(feat)
+        got = tfrecord.parse_example(rec)
+        assert got["name"] == [feat["name"]] and np.array_equal(got["xyz_pose"], feat["xyz_pose"])
+        assert np.array_equal(png.decode_png(got["png16"][0]), img)
+    assert recs and tfrecord.parse_example(recs[1])["bbx"].tolist() == [10.0, 20.0, 110.0, 140.0, 650.5]
+    back = T.read_bundle(os.path.join(gdir, "ckpt_small"))
+    want = G.tensors()
+    assert set(back) == set(want) and all(np.array_equal(back[k], want[k]) and back[k].shape == want[k].shape for k in want)
+    T.write_bundle(str(tmp_path / "ckpt_small"), want)
+    for ext in (".index", ".data-00000-of-00001"):
+        assert open(str(tmp_path / "ckpt_small") + ext, "rb").read() == open(os.path.join(gdir, "ckpt_small") + ext, "rb").read()
