@@ -395,6 +395,237 @@ wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   }
 }
 
+
+// ---- persistent 3xTF32 variant with the split A operand in TENSOR MEMORY (opt-in, DENSEREG_WGRAD_A_TMEM=1) ----------------------------------
+// As wgrad_tc_persist_kernel<true>, but the A tile (X^T, or dY^T when swapped) is split into tensor memory instead of shared memory: splitter
+// warp w owns tensor-memory lane quarter w % 4 = 32-channel chunk w % 4 of the tile (smem [chunk][pixel][32 channels]); for every pixel the
+// warp reads that pixel's 128 B row (conflict-free), so lane i collects channel i over the pixels = one K-major A row; hi / lo go out with
+// tcgen05.st and the MMAs use the [d], [a-tmem], b-desc form (A from tensor memory is K-major; B = the other operand stays MN-major in
+// shared memory and is split in place as before).  Two warps share a quarter and take 16 pixels (columns) each.
+// Shared-memory bytes per k-block at BN = 128: 32 KB TMA + 16 KB A reads + 48 KB B split + 48 KB B operand reads = 144 KB (224 KB before).
+DR_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192 + WG_SPLIT_THREADS, 1)
+wgrad_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.nchunks_b * WG_CHUNK_BYTES;
+  const int stage_bytes = WG_A_BYTES + 2 * b_bytes;                   // [A fp32 | B hi | B lo]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* split_bar = empty_bar + p.stages;
+  uint64_t* acc_full = split_bar + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.ksz * p.ksz * p.cin_tiles * p.n_tiles;
+  const int total_items = tiles * p.splits;
+  const uint32_t a_col0 = (2u * (uint32_t)p.BN + 31u) & ~31u;         // tensor-memory A ring behind the two accumulator stages
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], WG_SPLIT_THREADS / 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  struct Item { int tap, c0, n0, kb_begin, num_kb; };
+  auto decode = [&](int item) {
+    Item it;
+    const int split = item / tiles, tile = item - split * tiles;
+    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    it.tap = mt / p.cin_tiles;
+    it.c0 = (mt - it.tap * p.cin_tiles) * 128;
+    it.n0 = nt * p.BN;
+    it.kb_begin = split * p.kb_per_split;
+    int kb_end = it.kb_begin + p.kb_per_split;
+    if (kb_end > p.total_kb) kb_end = p.total_kb;
+    it.num_kb = kb_end - it.kb_begin;
+    return it;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(WG_A_BYTES + b_bytes);
+      uint32_t ring = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const Item w = decode(item);
+        const int dy = w.tap / p.ksz - p.pad, dx = w.tap % p.ksz - p.pad;
+        for (int i = 0; i < w.num_kb; ++i, ++ring) {
+          const int s = ring % p.stages;
+          const uint32_t ph = (ring / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int pix = (w.kb_begin + i) * WG_KB;
+          const int img = pix / (p.H * p.W);
+          const int rem = pix - img * p.H * p.W;
+          const int y = rem / p.W, x = rem - y * p.W;
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx);
+          if (!p.swap) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_4d(&map_x, &full_bar[s], st + j * WG_CHUNK_BYTES, w.c0 + 32 * j, x + dx, y + dy, img);
+            for (int j = 0; j < p.nchunks_b; ++j)
+              tma_load_4d(&map_dy, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, w.n0 + 32 * j, x, y, img);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_4d(&map_dy, &full_bar[s], st + j * WG_CHUNK_BYTES, w.c0 + 32 * j, x, y, img);
+            for (int j = 0; j < p.nchunks_b; ++j)
+              tma_load_4d(&map_x, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, w.n0 + 32 * j, x + dx, y + dy, img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // a_format = b_format = TF32, c = F32, a_major = K (A from tensor memory), b_major = MN (bit 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t ring = 0, tcount = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tcount) {
+        const Item w = decode(item);
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+        for (int i = 0; i < w.num_kb; ++i, ++ring) {
+          const int s = ring % p.stages;
+          const uint32_t ph = (ring / p.stages) & 1;
+          mbar_wait(&split_bar[s], ph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + WG_A_BYTES;
+          const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < WG_KB / 8; ++k) {
+            const uint64_t bd = make_desc_mn(b_addr + k * 1024, WG_CHUNK_BYTES, 512);
+            const uint64_t bld = make_desc_mn(b_addr + b_bytes + k * 1024, WG_CHUNK_BYTES, 512);
+            tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bld, idesc, (i | k) != 0);
+            tc_mma_tf32_ts(tmem_d, a_lo + 8u * k, bd, idesc, 1);
+            tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bd, idesc, 1);
+          }
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tcount) {
+      const Item w = decode(item);
+      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait_sleep(&acc_full[as], aph);
+      tc_fence_after();
+      const int c = w.c0 + q * 32 + lane;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.BN;
+      if (!p.swap) {
+        const bool cvalid = c < p.Cin;
+        float* row = p.dw + ((size_t)w.tap * p.Cin + c) * p.Cout;
+        for (int cb = 0; cb < p.BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)cb, v);
+          if (!cvalid) continue;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int n = w.n0 + cb + e;
+            if (n < p.Cout) atomicAdd(row + n, __uint_as_float(v[e]));
+          }
+        }
+      } else {
+        const bool cvalid = c < p.Cout;
+        float* col = p.dw + (size_t)w.tap * p.Cin * p.Cout + c;
+        for (int cb = 0; cb < p.BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)cb, v);
+          if (!cvalid) continue;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int n = w.n0 + cb + e;
+            if (n < p.Cin) atomicAdd(col + (size_t)n * p.Cout, __uint_as_float(v[e]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  } else {
+    // splitter warps 6..13: A -> tensor memory (quarter = warp % 4, pixel half = (warp - 6) / 4), B -> hi / lo in shared memory (all 256 threads)
+    const int t = threadIdx.x - 192;
+    const int q = warp & 3, half = (warp - 6) >> 2;
+    const int nb16 = b_bytes / 16;
+    uint32_t ring = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const Item w = decode(item);
+      for (int i = 0; i < w.num_kb; ++i, ++ring) {
+        const int s = ring % p.stages;
+        const uint32_t ph = (ring / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        // A: chunk q = 32 channels (lanes), pixels 16*half .. +15 (columns).  SWIZZLE_128B_ATOM_32B: within a 128 B pixel row the 32 B
+        // segment index is XORed with ((pixel >> 1) & 3)  [cute Layout_MN_SW128_32B_Atom: Swizzle<2,5,2> on bytes]
+        const uint8_t* achunk = st + (size_t)q * WG_CHUNK_BYTES;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) {
+          const int pix = half * 16 + pp;
+          const uint32_t off = (uint32_t)pix * 128u + (uint32_t)lane * 4u;
+          const uint32_t swz = off ^ ((off >> 2) & 0x60u);              // byte bits [5,6] ^= byte bits [7,8]
+          const float a = *reinterpret_cast<const float*>(achunk + swz);
+          const float h = tf32_rna(a);
+          hi[pp] = __float_as_uint(h); lo[pp] = __float_as_uint(tf32_rna(a - h));
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)s * 64u + (uint32_t)half * 16u;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        // B: elementwise split in place (hi) and into the lo copy
+        float4* bhi = reinterpret_cast<float4*>(st + WG_A_BYTES);
+        float4* blo = reinterpret_cast<float4*>(st + WG_A_BYTES + b_bytes);
+        for (int idx = t; idx < nb16; idx += WG_SPLIT_THREADS) {
+          float4 a = bhi[idx], h, l;
+          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
+          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
+          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
+          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
+          bhi[idx] = h; blo[idx] = l;
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 bool wgrad_tc_eligible(const WgradProblem& p) {
@@ -463,6 +694,30 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   cuuint64_t ys[3] = {(cuuint64_t)p.dy_cs * 4, (cuuint64_t)p.W * p.dy_cs * 4, (cuuint64_t)p.H * p.W * p.dy_cs * 4};
   if (!encode_map(&mdy, p.dy, 4, yd, ys, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 0;
 
+  static int atmem = -1;
+  if (atmem < 0) { const char* e = getenv("DENSEREG_WGRAD_A_TMEM"); atmem = (e && e[0] == '1') ? 1 : 0; }
+  if (atmem && split3 && BN <= 128) {
+    // A split into tensor memory: smem stage = A fp32 + B hi + B lo; tensor memory = 2*BN accumulator columns + 64 per ring stage
+    static bool aattr = false;
+    static int num_sms_a = 0;
+    if (!num_sms_a) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms_a, cudaDevAttrMultiProcessorCount, dev); if (num_sms_a <= 0) num_sms_a = 148; }
+    const int a_stage = WG_A_BYTES + 2 * t.nchunks_b * WG_CHUNK_BYTES;
+    const int a_col0 = (2 * BN + 31) / 32 * 32;
+    int a_stages = (208 * 1024) / a_stage;
+    if (a_stages > (512 - a_col0) / 64) a_stages = (512 - a_col0) / 64;
+    if (a_stages > 6) a_stages = 6;
+    if (a_stages >= 2) {
+      WgParams ta = t;
+      ta.stages = a_stages;
+      int acols = 32; while (acols < a_col0 + 64 * a_stages) acols <<= 1;
+      ta.tmem_cols = acols;
+      const int total_items = tiles * splits;
+      const size_t asmem = (size_t)a_stages * a_stage + (3 * a_stages + 4) * 8 + 16 + 1024 + 64;
+      if (!aattr) { cudaFuncSetAttribute(wgrad_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); aattr = true; }
+      wgrad_tc_atmem_kernel<<<dim3(total_items < num_sms_a ? total_items : num_sms_a), 192 + WG_SPLIT_THREADS, asmem, st>>>(mx, mdy, ta);
+      return 1;
+    }
+  }
   if (persist) {
     static bool pattr[2] = {false, false};
     static int num_sms = 0;

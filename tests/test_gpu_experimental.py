@@ -1,5 +1,6 @@
 """Opt-in kernels that have NOT been measured / verified on a B200 yet (written at the end of round 1 when the GPU budget was spent):
   DENSEREG_WGRAD_SWAP=2      wgrad with exchanged operand roles (M = cout, coalesced reductions)       wgrad_tc.cu
+  DENSEREG_WGRAD_A_TMEM=1    persistent wgrad with the split A operand in tensor memory                    wgrad_tc.cu
   DENSEREG_WGRAD_PERSIST=1   persistent wgrad kernel with double-buffered TMEM accumulators            wgrad_tc.cu
   DENSEREG_TC_STATS_PER_CTA=1  fused BRN statistics accumulated per CTA (one fence + counter per CTA)   conv_tc_epilogue.cuh
   DENSEREG_TC_PAIR_TAIL=1    pair conv kernel: last wave's items sliced along N over all clusters         conv_tc_pair.cu
@@ -21,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_SWAP": "2"}, {"DENSEREG_WGRAD_SWAP": "1"}, {"DENSEREG_WGRAD_PERSIST": "1"},
                                  {"DENSEREG_WGRAD_PERSIST": "1", "DENSEREG_WGRAD_SWAP": "1", "DENSEREG_WGRAD_WAVES": "4"},
-                                 {"DENSEREG_TC_STATS_PER_CTA": "1"}, {"DENSEREG_BRN_BLOCKS": "1184"}, {"DENSEREG_TC_PAIR_TAIL": "1"}, {"DENSEREG_POOL_BWD_V4": "1"}, {"DENSEREG_TC_A_TMEM": "2"}, {"DENSEREG_TC_A_TMEM": "1"}])
+                                 {"DENSEREG_TC_STATS_PER_CTA": "1"}, {"DENSEREG_BRN_BLOCKS": "1184"}, {"DENSEREG_TC_PAIR_TAIL": "1"}, {"DENSEREG_POOL_BWD_V4": "1"}, {"DENSEREG_TC_A_TMEM": "2"}, {"DENSEREG_TC_A_TMEM": "1"}, {"DENSEREG_WGRAD_A_TMEM": "1"},
+                                 {"DENSEREG_WGRAD_A_TMEM": "1", "DENSEREG_WGRAD_SWAP": "1"}])
 def test_parity_suite_with_switch(env):
     e = dict(os.environ, **env)
     e.pop("DENSEREG_TEST_EXPERIMENTAL", None)

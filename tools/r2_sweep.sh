@@ -16,6 +16,8 @@ run base DENSEREG_NOP=1
 run brn_blocks_1184 DENSEREG_BRN_BLOCKS=1184      # round-1 measured setting (reduce AND apply); default is now 296 for the reduce kernel only
 run brn_blocks_592 DENSEREG_BRN_BLOCKS=592
 run stats_per_cta DENSEREG_TC_STATS_PER_CTA=1
+run wgrad_a_tmem DENSEREG_WGRAD_A_TMEM=1
+run wgrad_a_tmem_swap DENSEREG_WGRAD_A_TMEM=1 DENSEREG_WGRAD_SWAP=1
 run a_tmem_1 DENSEREG_TC_A_TMEM=1
 run a_tmem_2 DENSEREG_TC_A_TMEM=2
 run pool_bwd_v4 DENSEREG_POOL_BWD_V4=1
