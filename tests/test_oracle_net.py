@@ -103,3 +103,46 @@ def test_net_golden_statistics():
     hms, hm3s, ums = net.forward(p, s, x0, training=False)
     np.testing.assert_allclose(hms[0].numpy()[0, ::4, ::4], g["hm_sub"], rtol=2e-4, atol=1e-6)
     np.testing.assert_allclose(ums[0].numpy()[0, ::4, ::4], g["um_sub"], rtol=2e-4, atol=1e-6)
+
+
+def test_c_abi_error_behaviour_without_a_gpu(built_lib):
+    """Argument and call-order checks of the C-ABI happen before any CUDA call, so they are testable here: bad arguments -> DR_ERR_ARG (-1),
+    wrong call order -> DR_ERR_STATE (-3) with a message from dr_last_error; nothing throws across the boundary."""
+    from densereg_b200 import _ffi
+    lib = built_lib
+    h = C.c_void_p()
+    ok = dict(num_stack=2, num_fea=128, kernel_size=3, num_jnt=16, in_hw=128, out_hw=32, max_batch=4, precision=0, device=0)
+    for bad in (dict(kernel_size=5), dict(in_hw=256), dict(out_hw=64), dict(num_stack=0), dict(num_stack=5), dict(num_fea=6), dict(num_fea=130),
+                dict(num_jnt=0), dict(num_jnt=65), dict(max_batch=0)):
+        cfg = _ffi.DrConfig(**dict(ok, **bad))
+        assert lib.dr_create(C.byref(h), C.byref(cfg)) == -1, bad
+        assert not h.value
+    assert lib.dr_create(None, None) == -1
+    cfg = _ffi.DrConfig(**ok)
+    assert lib.dr_create(C.byref(h), C.byref(cfg)) == 0 and h.value
+    li = _ffi.DrLayerInfo()
+    assert lib.dr_get_layer(h, -1, C.byref(li)) == -1 and lib.dr_get_layer(h, lib.dr_num_layers(h), C.byref(li)) == -1
+    assert lib.dr_get_layer(h, 0, None) == -1
+    assert lib.dr_bind(h, None, None, None, None, None) == -1                      # params and state are mandatory
+    fake = C.c_void_p(0x1000)                                                      # never dereferenced: every call below fails its checks first
+    # call order: nothing bound yet
+    assert lib.dr_init_params(h, 0, C.c_float(0.01), None) == -3 and b"dr_bind" in lib.dr_last_error(h)
+    assert lib.dr_debug_conv(h, 0, 1, fake, fake, 0, None) == -3
+    # no gradient / Adam buffers bound: the training entry points refuse
+    assert lib.dr_loss_backward(h, 1, fake, fake, fake, fake, fake, 0, 1, None) == -3 and b"grads" in lib.dr_last_error(h)
+    assert lib.dr_zero_grads(h, None) == -3
+    assert lib.dr_optimizer_step(h, 5, 1, C.c_float(1e-3), 1, None) == -3
+    # argument checks
+    assert lib.dr_optimizer_step(h, 0, 1, C.c_float(1e-3), 1, None) == -1 and lib.dr_optimizer_step(h, 5, 0, C.c_float(1e-3), 1, None) == -1
+    assert lib.dr_infer(h, 1, None, fake, fake, fake, None, None) == -1
+    assert lib.dr_loss_backward(h, 1, None, fake, fake, fake, fake, 0, 1, None) == -1
+    assert lib.dr_vote(h, 1, 32, 32, 65, fake, fake, fake, fake, fake, fake, fake, None, None, None) == -1             # J > 64
+    assert lib.dr_vote(h, 1, 2, 2, 16, fake, fake, fake, fake, fake, fake, fake, None, None, None) == -1               # fewer than 5 pixels: no top-5
+    assert lib.dr_norm_dm(h, 0, 128, fake, fake, fake, None) == -1
+    assert lib.dr_debug_conv(h, 10 ** 6, 1, fake, fake, 0, None) == -1
+    assert lib.dr_data_aug(h, 1, 128, 16, fake, fake, fake, fake, fake, fake, fake, None, None) == -1                   # null output
+    # binding needs a device: on a GPU-less machine it reports a CUDA error code instead of crashing
+    import torch
+    rc = lib.dr_bind(h, fake, fake, None, None, None)
+    assert rc == 0 if torch.cuda.is_available() else rc in (0, -2)
+    assert lib.dr_destroy(h) == 0
