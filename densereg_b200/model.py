@@ -121,6 +121,43 @@ def format_result_row(name, xyz_val):
     return res_str.replace("/", "\\")
 
 
+def read_result_file(path):
+    """Rows written by test() / model/test_model.py:70-76 (`name\\t%.4f\\t...`, '/' stored as '\\\\') -> ([names], (N, 3J) float64 array).  Reads the reference's
+    published exp/result/{icvl,nyu,msra}.txt as well as this repo's files."""
+    names, rows = [], []
+    with open(path) as f:
+        for ln, line in enumerate(f, 1):
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            parts = line.split("\t")
+            if len(parts) < 4 or (len(parts) - 1) % 3:
+                raise ValueError("%s:%d: expected name + 3J tab-separated values, got %d fields" % (path, ln, len(parts)))
+            names.append(parts[0].replace("\\", "/"))
+            rows.append([float(v) for v in parts[1:]])
+    if rows and len({len(r) for r in rows}) != 1:
+        raise ValueError("%s: rows with different joint counts" % path)
+    return names, np.asarray(rows, np.float64)
+
+
+def compare_result_files(path_a, path_b):
+    """Frame-by-frame comparison of two result files (e.g. the reference's exp/result/icvl.txt and a run of this engine restored from the authors'
+    checkpoint): frames are matched by name; returns mean / max joint distance (mm) and the evaluation.py error curve of the per-frame maxima."""
+    na, a = read_result_file(path_a)
+    nb, b = read_result_file(path_b)
+    ib = {n: i for i, n in enumerate(nb)}
+    common = [(i, ib[n]) for i, n in enumerate(na) if n in ib]
+    if not common:
+        raise ValueError("no frame names in common")
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("different joint counts: %d vs %d values per row" % (a.shape[1], b.shape[1]))
+    mean_e = [meanJntError(a[i], b[j]) for i, j in common]
+    max_e = [maxJntError(a[i], b[j]) for i, j in common]
+    within, curve = error_curve(max_e)
+    return {"frames": len(common), "only_in_a": len(na) - len(common), "only_in_b": len(nb) - len(common),
+            "mean_joint_dist_mm": float(np.mean(mean_e)), "max_joint_dist_mm": float(np.max(max_e)), "within_mm": within, "curve": curve}
+
+
 class JointDetectionModel:
     """Same public attributes as the reference object (hourglass_um_crop_tiny.py:66-191, 436-543)."""
     _init_lr = 0.001

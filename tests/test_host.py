@@ -135,3 +135,31 @@ def test_dataset_switch_and_checkpoint_flags(tmp_path):
     assert f2.restore_step == -1 and f2.pid == 3
     tr, te = M.open_datasets(f2, log=logs.append)
     assert tr.name == "msra_P3" and tr.jnt_num == 21 and te.exact_num == 8488
+
+
+def test_result_file_reader_and_comparison(tmp_path):
+    """read_result_file parses the reference's exp/result format (fixture rows) and this repo's writer; compare_result_files matches frames by name."""
+    from densereg_b200 import model as M
+    rows = {}
+    for line in open(os.path.join(GOLD, "result_format_rows.txt")):
+        ds, row = line.rstrip("\n").split("|", 1)
+        rows.setdefault(ds, []).append(row)
+    for ds, J in (("icvl", 16), ("nyu", 14), ("msra", 21)):
+        p = tmp_path / (ds + ".txt")
+        p.write_text("\n".join(rows[ds]) + "\n")
+        names, arr = M.read_result_file(str(p))
+        assert arr.shape == (len(rows[ds]), 3 * J) and "\\" not in names[0] and (ds == "nyu" or "/" in names[0])       # NYU names have no directory
+        # our writer round-trips the same rows byte for byte
+        q = tmp_path / (ds + "_b200.txt")
+        q.write_text("".join(M.format_result_row(n, v) for n, v in zip(names, arr)))
+        assert q.read_text() == p.read_text()
+        # shift every joint of the second file by (3, 4, 0) mm -> 5 mm joint distance everywhere; drop the last frame
+        shifted = arr + np.tile([3.0, 4.0, 0.0], J)
+        q.write_text("".join(M.format_result_row(n, v) for n, v in zip(names[:-1], shifted[:-1])))
+        c = M.compare_result_files(str(p), str(q))
+        assert c["frames"] == len(names) - 1 and c["only_in_a"] == 1 and c["only_in_b"] == 0
+        assert abs(c["mean_joint_dist_mm"] - 5.0) < 1e-3 and abs(c["max_joint_dist_mm"] - 5.0) < 1e-3 and c["within_mm"][10] == 1.0
+        assert c["curve"][1] == (5.5, 100.0) and c["curve"][0] == (0.5, 0.0)
+    bad = tmp_path / "bad.txt"; bad.write_text("name\t1.0\t2.0\n")
+    with pytest.raises(ValueError):
+        M.read_result_file(str(bad))
