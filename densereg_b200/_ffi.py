@@ -36,6 +36,7 @@ SIGNATURES = {
     "dr_num_layers": (C.c_int, [_P]),
     "dr_get_layer": (C.c_int, [_P, C.c_int, C.POINTER(DrLayerInfo)]),
     "dr_bind": (C.c_int, [_P, _F, _F, _F, _F, _F]),
+    "dr_params_changed": (C.c_int, [_P]),
     "dr_init_params": (C.c_int, [_P, C.c_uint64, C.c_float, _P]),
     "dr_norm_dm": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _P]),
     "dr_forward": (C.c_int, [_P, C.c_int, _F, _F, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

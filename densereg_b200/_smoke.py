@@ -1,5 +1,7 @@
-"""smoke(): one tiny invocation of the hot path on cuda:0, checked against the CPU oracle
-(forward + vote, and one training micro-step)."""
+"""smoke(): small invocations of the hot path on cuda:0, checked against the CPU oracle: forward + vote and one training micro-step on the
+1-stack / 64-feature net, then one training micro-step of the benchmarked configuration (2-stack, 128 features, batch 32) so that the
+tcgen05 kernels bench.py times (one-CTA and CTA-pair conv, tensor-core wgrad) are exercised here too.  Everything runs in the library's
+default arithmetic (3xTF32 on the tensor cores)."""
 import numpy as np
 import torch
 
@@ -39,3 +41,23 @@ def run():
           % (e_map, e_xyz, e_loss, e_grad, eng.launch_count))
     # gradient bar: 2e-2 -- two fp32 evaluations of this graph differ by ~3e-3 (ReLU/BRN sign flips; see tests/test_gpu_net.py)
     assert e_map < 1e-4 and e_xyz <= 1e-3 and e_loss < 1e-4 and e_grad < 2e-2
+    assert eng.tc_launch_count > 0, "the tensor-core path did not run"
+    eng.close()
+    # ---- the benchmarked configuration: 2-stack fea=128, batch 32 (>= 64 work items per big layer -> CTA-pair kernel)
+    S, F, J, B = 2, 128, 16, 32
+    eng = DenseRegEngine(S, F, J, max_batch=B, training=True, precision="tf32x3")
+    net = U.Net(S, F, J)
+    p, s = net.init_params(0, stddev=0.05), net.init_state()
+    eng.load_flat(p, s)
+    dms, poses, cfgs, coms = synth.make_batch(B, J, seed=2)
+    d, po, cf, co = cu(dms), cu(poses), cu(cfgs), cu(coms)
+    eng.zero_grads()
+    tc0 = eng.tc_launch_count
+    loss = eng.loss_backward(d, po, cf, co, dropout_seed=4).cpu().numpy()
+    L, g_ref, _ = U.loss_and_grads(net, p, s.clone(), dms[..., 0], poses, cfgs, coms, dropout_seed=4)
+    e_loss = abs(loss[0] - L["total"]) / abs(L["total"])
+    e_grad = float((eng.grads.cpu() - g_ref).norm() / g_ref.norm())
+    n_tc = eng.tc_launch_count - tc0
+    print("smoke: 2x128 B=%d 3xTF32 micro-step: loss relerr %.2e | grad relerr %.2e | tensor-core launches %d of %d"
+          % (B, e_loss, e_grad, n_tc, eng.launch_count))
+    assert e_loss < 1e-4 and e_grad < 2e-2 and n_tc > 300

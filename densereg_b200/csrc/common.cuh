@@ -57,6 +57,7 @@ int launch_conv_simt(const ConvProblem& p, cudaStream_t st);
 int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st);
 
 // tcgen05 path (conv_tc.cu). Returns 0 launches if the problem shape is not eligible.
+const char* tc_last_error();     // why the last tensor-core launch of this thread returned 0 launches
 bool conv_tc_eligible(const ConvProblem& p);
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st);
 // CTA-pair (cta_group::2) 3xTF32 variant (conv_tc_pair.cu), opt-in (ConvProblem::pair); same contract as launch_conv_tc

@@ -47,6 +47,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  // Two-level accumulation (p.chunk_kb > 0): the tensor core's fp32 accumulate truncates, which biases long reductions (measured 1.6e-5 of
+  // the output scale at K = 2304 against 3e-7 for FFMA).  The k-blocks of a tile are therefore cut into chunks of `ch`; each chunk is summed
+  // by the MMAs into one of the two partial accumulator stages (first MMA of the chunk overwrites), and the epilogue warps add finished
+  // partials into a running sum held in tensor memory (columns 2*BN ...) with round-to-nearest fp32 adds while the MMAs fill the other
+  // stage.  The last partial is combined with the running sum on the fly by tc_epilogue_tile.  Tiles with num_kb <= ch are unchanged.
+  const int ch = (p.chunk_kb > 0 && num_kb > p.chunk_kb) ? p.chunk_kb : num_kb;
+  const int nchunks = (num_kb + ch - 1) / ch;
+  const uint32_t run_col = 2u * (uint32_t)p.BN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], SPLIT_THREADS / 32); }
@@ -93,34 +101,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);            // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, ccount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++ccount) {
+          const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+          mbar_wait(&acc_empty[as], aph ^ 1);            // epilogue has drained this accumulator stage
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
+          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+          const int kb0 = c * ch, kb1 = kb0 + ch < num_kb ? kb0 + ch : num_kb;
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t b_addr = a_addr + (SPLIT3 ? 2 : 1) * A_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t ad = make_desc(a_addr + k * 32), bd = make_desc(b_addr + k * 32);
-            if (SPLIT3) {
-              const uint64_t ald = make_desc(a_addr + A_TILE_BYTES + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
-              tc_mma_tf32(tmem_d, ad, bld, idesc, (kb | k) != 0);      // hi * lo
-              tc_mma_tf32(tmem_d, ald, bd, idesc, 1);                  // lo * hi
-              tc_mma_tf32(tmem_d, ad, bd, idesc, 1);                   // hi * hi
-            } else {
-              tc_mma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t ad = make_desc(a_addr + k * 32), bd = make_desc(b_addr + k * 32);
+              const uint32_t acc = ((kb - kb0) | k) != 0;                // first MMA of a chunk overwrites the partial accumulator
+              if (SPLIT3) {
+                const uint64_t ald = make_desc(a_addr + A_TILE_BYTES + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
+                tc_mma_tf32(tmem_d, ad, bld, idesc, acc);                // hi * lo
+                tc_mma_tf32(tmem_d, ald, bd, idesc, 1);                  // lo * hi
+                tc_mma_tf32(tmem_d, ad, bd, idesc, 1);                   // hi * hi
+              } else {
+                tc_mma_tf32(tmem_d, ad, bd, idesc, acc);
+              }
             }
+            tc_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
           }
-          tc_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+          tc_commit(&acc_full[as]);              // partial accumulator complete -> epilogue warps
         }
-        tc_commit(&acc_full[as]);              // accumulator complete -> epilogue
       }
     }
   } else if (warp < 6) {
@@ -135,14 +147,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     tc_epilogue_stage_affine(p, et, s_scale, s_shift);
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t ccount = 0;
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
-      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-      mbar_wait_sleep(&acc_full[as], aph);
-      tc_fence_after();
-      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
-                       s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
+      for (int c = 0; c < nchunks; ++c, ++ccount) {
+        const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+        mbar_wait_sleep(&acc_full[as], aph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.BN;
+        if (c + 1 < nchunks) {
+          // flush: running (+)= partial, this warp's 32 lanes, round-to-nearest fp32 adds; then hand the stage back to the MMA warp
+          for (int cb = 0; cb < p.BN; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + lane_bits + (uint32_t)cb, v);
+            if (c > 0) {
+              uint32_t r2[32];
+              tmem_ld32(tmem_base + lane_bits + run_col + (uint32_t)cb, r2);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(r2[i]), __uint_as_float(v[i])));
+            }
+            tmem_st32(tmem_base + lane_bits + run_col + (uint32_t)cb, v);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        } else {
+          tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
+                           s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); }, tmem_base + run_col, nchunks > 1);
+        }
+      }
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
   } else if (SPLIT3) {
@@ -186,6 +221,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // that copy when ConvProblem::w_kmajor is set).  Eligibility: stride 1, k in {1,3}, square power-of-two maps that tile
 // into whole rows (W <= 128, 128 % W == 0), input view 16 B aligned with a channel stride that is a multiple of 4 floats (Cin itself may be ragged: 131, 65, 515 ...;
 // TMA zero-fills the channel tail of both operands).
+const char* tc_last_error() { return tc::last_error(); }
+
 bool conv_tc_eligible(const ConvProblem& p) {
   if (!p.w_kmajor) return false;
   if (p.stride != 1 || (p.k != 1 && p.k != 3)) return false;
@@ -206,19 +243,22 @@ bool conv_tc_eligible(const ConvProblem& p) {
 
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
-  if (split3) {
+  // two-level accumulation (kernel comment): DENSEREG_TC_CHUNK = k-blocks per partial accumulator, 0 = off.  3xTF32 only; chunked layers
+  // run on this kernel (the CTA-pair kernel's tensor memory is full with two 256-column accumulator stages).
+  static int chunk_kb = -1;
+  if (chunk_kb < 0) { const char* e = getenv("DENSEREG_TC_CHUNK"); chunk_kb = e ? atoi(e) : 0; if (chunk_kb < 0) chunk_kb = 0; }
+  const int num_kb_all = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
+  const bool chunked = split3 && chunk_kb > 0 && num_kb_all > chunk_kb;
+  if (split3 && !chunked) {
     const bool pair_w = conv_tc_pair_wanted(p);
     const int am = conv_tc_atmem_mode();                   // opt-in: split A operand in tensor memory (conv_tc_atmem.cu)
     if (am == 2 || (am == 1 && !pair_w)) {
       const int n = launch_conv_tc_atmem(p, st);
-      if (n > 0) return n;
+      if (n > 0) return n;                                 // 0 = shape not taken by that variant (no launch attempted)
     }
-    if (pair_w) {                                          // CTA-pair kernel for the big layers; falls through if its launch fails
-      const int n = launch_conv_tc_pair(p, st);
-      if (n > 0) return n;
-    }
+    if (pair_w) return launch_conv_tc_pair(p, st);         // CTA-pair kernel for the big layers; a failed launch is an error, not a reason to run another kernel
   }
-  TcParams t;
+  TcParams t; memset(&t, 0, sizeof(t));
   t.M = p.B * p.H * p.W; t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t; t.flip_taps = p.flip_taps;
   int BN = (p.Cout + 15) / 16 * 16;
   if (BN > 256) BN = 256;
@@ -227,8 +267,9 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
     if (bn_cap >= 16 && BN > bn_cap) BN = bn_cap / 16 * 16; }
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
-  int cols = 32; while (cols < 2 * BN) cols <<= 1;         // two accumulator stages
+  int cols = 32; while (cols < (chunked ? 2 * BN + (BN + 31) / 32 * 32 : 2 * BN)) cols <<= 1;   // two accumulator stages (+ the running sum)
   t.tmem_cols = cols;
+  t.chunk_kb = chunked ? chunk_kb : 0;
   t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;
   const int stage_bytes = (split3 ? 2 : 1) * (A_TILE_BYTES + BN * TC_BK * 4);
   // shared-memory budget: 227 KB per CTA minus the kernel's static part (statistics staging + scale/shift tables), barriers, alignment slack
@@ -278,9 +319,10 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   if (split3) {
     if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[1] = true; }
     conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+    return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<3xTF32>") ? 1 : 0;
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[0] = true; }
     conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
   }
-  return 1;
+  return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<TF32>") ? 1 : 0;
 }

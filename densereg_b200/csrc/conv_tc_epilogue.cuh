@@ -30,6 +30,8 @@ struct TcParams {
   int full_items, tail_f;  // pair kernel: items >= full_items are 1/tail_f-wide N slices of the last wave's items (tail_f = 1: off)
   int stats_per_cta;     // fused BRN statistics: accumulate per CTA in shared memory, ONE round of atomics + fence + counter per CTA (opt-in)
   int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
+  int chunk_kb;          // > 0: two-level accumulation -- the tensor core sums at most chunk_kb k-blocks into a partial accumulator (its fp32 adds
+                         // truncate), partials are added into a running sum with round-to-nearest fp32 adds by the epilogue warps (conv_tc.cu)
 };
 constexpr int TC_STAGE_LD = 36;      // floats per staging row: 16 B aligned, conflict-free for float4 writes (row per lane) and row reads
 
@@ -61,10 +63,12 @@ DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scal
 // 32-column chunk, and the residual / accumulate operands of a chunk are fetched as one batch of independent 16 B loads, so the chunk
 // is a straight line of independent instructions (the first version interleaved two dependent global loads and four branches per
 // element: 0.1 instructions per cycle per warp, 12 us per 128x128 tile -- profiles/r1_epilogue.md).
+// tmem_acc2 / has2: a second accumulator (same lanes / column layout) whose values are ADDED (fp32, round to nearest) to the first one before
+// anything else -- the running sum of the earlier K chunks in the two-level accumulation mode.
 template <class Release>
 DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0, int bn,
                                 int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, float* s_scale,
-                                float* s_shift, float* stg, Release release) {
+                                float* s_shift, float* stg, Release release, uint32_t tmem_acc2 = 0, bool has2 = false) {
     const int m = tile_m * TC_BM + row;
     const bool mvalid = m < p.M;
     float* yr = p.y + (size_t)m * p.y_cs;
@@ -73,6 +77,12 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     for (int cb = 0; cb < bn; cb += 32) {          // bn = columns of this work item (p.BN, or a slice of it in the pair kernel's tail)
       uint32_t v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+      if (has2) {
+        uint32_t r2[32];
+        tmem_ld32(tmem_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(r2[i]), __uint_as_float(v[i])));
+      }
       if (p.stats) {
         // column sums over this warp's 32 rows by recursive halving: 31 shuffles, lane l ends with column cb+l
         float a[32], b2[32];

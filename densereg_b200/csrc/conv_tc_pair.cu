@@ -264,7 +264,7 @@ bool conv_tc_pair_wanted(const ConvProblem& p) {
 // Same contract as launch_conv_tc (conv_tc.cu) with split3 = 1; the caller has checked conv_tc_eligible(p).
 int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   static bool attr_set = false;
-  TcParams t;
+  TcParams t; memset(&t, 0, sizeof(t));
   t.M = p.B * p.H * p.W; t.H = p.H; t.W = p.W; t.Cin = p.Cin; t.Cout = p.Cout; t.ksz = p.k; t.pad = p.pad_t; t.flip_taps = p.flip_taps;
   int BN = (p.Cout + 15) / 16 * 16;
   if (BN > 256) BN = 256;
@@ -329,7 +329,7 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
     }
   }
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
+    if (!tc::launch_ok(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536), "conv_tc_pair_kernel smem attribute")) return 0;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
@@ -338,6 +338,5 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, mwt, mwlot, t) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return 1;
+  return tc::launch_ok(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, mwt, mwlot, t), "conv_tc_pair_kernel") ? 1 : 0;
 }

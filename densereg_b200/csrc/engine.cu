@@ -79,6 +79,9 @@ struct dr_handle {
   std::string err;
   int precision = 0;
   int64_t tc_launches = 0;
+  // aligned / split weight copies are rebuilt only when the parameters changed (dr_optimizer_step, dr_init_params, dr_bind,
+  // dr_params_changed) or another arithmetic mode asks for them -- not once per micro-batch
+  bool weights_dirty = true; int prepped_precision = -1; bool prep_once = true;
   // backward: filter gradients run on a side stream (they only feed the optimiser) so that they fill the SMs the small
   // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
   static const int kScratchSlots = 3;
@@ -107,6 +110,14 @@ namespace {
 
 inline int fail(dr_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
 
+// add the launch count of a run_conv / run_wgrad call, or propagate its (negative) error code
+#define RUN_TRY(acc, expr)                  \
+  do {                                      \
+    const int n__ = (expr);                 \
+    if (n__ < 0) return n__;                \
+    (acc) += n__;                           \
+  } while (0)
+
 int same_pad_before(int n, int k, int s) {
   int out = (n + s - 1) / s;
   int total = (out - 1) * s + k - n;
@@ -120,6 +131,7 @@ int same_pad_before(int n, int k, int s) {
 struct Builder {
   dr_handle* h;
   int F, J, S;
+  bool plan_overflow = false;
   int new_buf(int hw, int C, int raw = 0) {
     Buf b; b.H = hw; b.W = hw; b.C = C; b.Cs = C == 1 ? 1 : (C + 3) / 4 * 4; b.raw = raw;   // 1-channel maps stay dense
     size_t& total = raw ? h->raw_per_crop : h->act_per_crop;
@@ -265,6 +277,7 @@ struct Builder {
           int c0 = c;
           while (c < v.C && !written[v.buf][v.coff + c]) ++c;
           if (g.nfill < 4) { View f; f.buf = v.buf; f.coff = v.coff + c0; f.C = c - c0; g.fill[g.nfill++] = f; }
+          else plan_overflow = true;               // more unwritten channel gaps than GradWrite can zero-fill: dr_create fails
         }
       }
       mark(v);
@@ -388,17 +401,22 @@ struct TraceScope {
   }
 };
 
+// A problem the tensor-core path accepts (conv_tc_eligible / wgrad_tc_eligible) MUST run there: a failed tensor-map encode or launch is an
+// error (negative return, message in dr_last_error), never a quiet switch to the FFMA kernels.
 int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
   TraceScope tr(st);
   if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) {
     ConvProblem q = p;
     q.pair = p.pair ? p.pair : (h->tc_pair ? 1 : 0);
     int n = launch_conv_tc(q, precision == DR_PREC_TF32X3, st);
-    if (n > 0) {
-      h->tc_launches += n;
-      tr.done(p.flip_taps ? "dgrad" : "conv", p.B, p.H, p.Cin, p.Cout, p.k, (precision == DR_PREC_TF32X3 && conv_tc_pair_wanted(q)) ? "pair" : "tc");
-      return n;
+    if (n <= 0) {
+      char msg[256];
+      snprintf(msg, sizeof(msg), "tensor-core conv launch failed (B=%d HW=%d Cin=%d Cout=%d k=%d): %s", p.B, p.H, p.Cin, p.Cout, p.k, tc_last_error());
+      return fail(h, DR_ERR_CUDA, msg);
     }
+    h->tc_launches += n;
+    tr.done(p.flip_taps ? "dgrad" : "conv", p.B, p.H, p.Cin, p.Cout, p.k, (precision == DR_PREC_TF32X3 && conv_tc_pair_wanted(q)) ? "pair" : "tc");
+    return n;
   }
   int n = launch_conv_simt(p, st);
   tr.done(p.flip_taps ? "dgrad" : "conv", p.B, p.H, p.Cin, p.Cout, p.k, "simt");
@@ -409,7 +427,13 @@ int run_wgrad(dr_handle* h, const WgradProblem& p, int precision, cudaStream_t s
   TraceScope tr(st);
   if (precision != DR_PREC_FP32 && wgrad_tc_eligible(p)) {
     int n = launch_wgrad_tc(p, precision == DR_PREC_TF32X3, st);
-    if (n > 0) { h->tc_launches += n; tr.done("wgrad", p.B, p.H, p.Cin, p.Cout, p.k, "tc"); return n; }
+    if (n <= 0) {
+      char msg[256];
+      snprintf(msg, sizeof(msg), "tensor-core wgrad launch failed (B=%d HW=%d Cin=%d Cout=%d k=%d): %s", p.B, p.H, p.Cin, p.Cout, p.k, tc_last_error());
+      return fail(h, DR_ERR_CUDA, msg);
+    }
+    h->tc_launches += n; tr.done("wgrad", p.B, p.H, p.Cin, p.Cout, p.k, "tc");
+    return n;
   }
   int n = launch_wgrad_simt(p, st);
   tr.done("wgrad", p.B, p.H, p.Cin, p.Cout, p.k, "simt");
@@ -433,6 +457,18 @@ int prep_weights(dr_handle* h, int precision, cudaStream_t st) {
   prep_weights_kernel<<<dim3((unsigned)h->layers.size(), 48), 256, 0, st>>>(h->ltab, h->params, h->wk, h->wa, h->wk_hi, h->wk_lo,
                                                                            h->wa_hi, h->wa_lo, split);
   ++h->launches;
+  return DR_OK;
+}
+
+// prep_weights only when needed: parameters changed since the last build, or the mode needs the hi / lo split and only the plain copies exist
+int ensure_prepped(dr_handle* h, int precision, cudaStream_t st) {
+  const int need = precision == DR_PREC_TF32X3 ? 2 : 1;
+  const int have = h->prepped_precision == DR_PREC_TF32X3 ? 2 : (h->prepped_precision >= 0 ? 1 : 0);
+  if (h->prep_once && !h->weights_dirty && have >= need) return DR_OK;
+  const int prec = (have > need && h->prep_once) ? h->prepped_precision : precision;     // keep the split copies current once they exist
+  int rc = prep_weights(h, prec, st);
+  if (rc) return rc;
+  h->weights_dirty = false; h->prepped_precision = prec;
   return DR_OK;
 }
 
@@ -504,7 +540,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
   if (ud.n > 8) return fail(h, DR_ERR_UNSUPPORTED, "num_stack > 4 not supported");
   for (int i = 0; i < ud.n; ++i) { ud.p[i] = X.ptr(h->uvd_dst[i]); ud.cs[i] = X.cs(h->uvd_dst[i]); }
   nl += launch_make_uvd(B, IN, OUT, x0, tiny, ud, st);
-  if (training || h->precision != DR_PREC_FP32) { rc = prep_weights(h, h->precision, st); if (rc) return rc; }
+  if (training || h->precision != DR_PREC_FP32) { rc = ensure_prepped(h, h->precision, st); if (rc) return rc; }
   if (training) {
     CUDA_TRY(h, cudaMemsetAsync(h->sums, 0, h->n_sums * sizeof(double), st));
     CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, h->layers.size() * sizeof(unsigned int), st));
@@ -533,9 +569,8 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
             p.stats = sums; p.stats_counter = h->counters + o.layer; p.bn_bg = h->params + L.p_off; p.bn_state = h->state + L.s_off;
             p.bn_aff = h->aff + L.aff_off; p.bn_bstat = h->bstat + L.bstat_off; p.bn_update_state = update_state;
           }
-          const int64_t tc_before = h->tc_launches;
-          nl += run_conv(h, p, h->precision, st);
-          if (!fuse || h->tc_launches == tc_before)      // SIMT path (or a failed tensor-map encode): separate statistics pass
+          RUN_TRY(nl, run_conv(h, p, h->precision, st));
+          if (!fuse)                                     // SIMT path: separate statistics pass
             nl += launch_channel_stats_finalize(X.npix(rv), L.cout, p.y, p.y_cs, sums, h->counters + o.layer, h->params + L.p_off,
                                                 h->state + L.s_off, h->aff + L.aff_off, h->bstat + L.bstat_off, update_state, st);
           nl += launch_brn_apply(X.npix(rv), L.cout, p.y, p.y_cs, aff, L.relu, res, res_cs, X.ptr(o.out), X.cs(o.out), st);
@@ -545,7 +580,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
           else { p.scale = nullptr; p.shift = h->params + L.p_off; }
           p.relu = L.relu; p.res = res; p.res_cs = res_cs; p.accumulate = o.accumulate;
           if (training && o.dropout_tag >= 0) { p.dropout = 1; p.drop_seed = dropout_seed; p.drop_tag = (uint32_t)o.dropout_tag; }
-          nl += run_conv(h, p, h->precision, st);
+          RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
         break;
       }
@@ -633,10 +668,10 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         if (h->side_stream) {
           CUDA_TRY(h, cudaEventRecord(h->ev_ready[slot], st));
           CUDA_TRY(h, cudaStreamWaitEvent(h->wgrad_stream, h->ev_ready[slot], 0));
-          nl += run_wgrad(h, wp, h->precision, h->wgrad_stream);
+          RUN_TRY(nl, run_wgrad(h, wp, h->precision, h->wgrad_stream));
           CUDA_TRY(h, cudaEventRecord(h->ev_wdone[slot], h->wgrad_stream));
         } else {
-          nl += run_wgrad(h, wp, h->precision, st);
+          RUN_TRY(nl, run_wgrad(h, wp, h->precision, st));
         }
         if (o.need_dgrad) {
           nl += apply_fills(h, X, o.gw_in, st);
@@ -646,7 +681,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
           set_dgrad_weights(h, L, h->precision, p);
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
-          nl += run_conv(h, p, h->precision, st);
+          RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
         break;
       }
@@ -729,8 +764,10 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   h->precision = cfg->precision;
   // CTA-pair (cta_group::2) 3xTF32 kernel for the big layers: on by default; dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0 turns it off
   { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] >= 0 && !(env && env[0] == '0'); }
+  { const char* env = getenv("DENSEREG_PREP_ONCE"); h->prep_once = !(env && env[0] == '0'); }
   Builder b{h, 0, 0, 0};
   b.build();
+  if (b.plan_overflow) { delete h; return DR_ERR_UNSUPPORTED; }   // a gradient view with > 4 unwritten channel gaps (never on um_v1)
   *out = h;
   return DR_OK;
 }
@@ -785,7 +822,14 @@ int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out) {
 int dr_bind(dr_handle* h, float* params, float* state, float* grads, float* adam_m, float* adam_v) {
   if (!h || !params || !state) return DR_ERR_ARG;
   h->params = params; h->state = state; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
+  h->weights_dirty = true;
   return init_device(h);
+}
+
+int dr_params_changed(dr_handle* h) {
+  if (!h) return DR_ERR_ARG;
+  h->weights_dirty = true;
+  return DR_OK;
 }
 
 int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream) {
@@ -794,6 +838,7 @@ int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   h->launches += launch_init_trunc_normal(h->n_params, h->params, stddev, seed, st);
   init_state_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state); ++h->launches;
+  h->weights_dirty = true;
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
@@ -862,6 +907,7 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
     CUDA_TRY(h, cudaGetLastError());
     return DR_OK;
   }
+  if (h->precision != DR_PREC_FP32) { int rc = ensure_prepped(h, h->precision, st); if (rc) return rc; }   // never inside the captured graph
   dr_handle::InferGraph& g = h->infer_graph;
   const bool same = g.B == B && g.dm == dm_mm && g.cfg == cfgs && g.com == coms && g.xyz == xyz_mm && g.top5 == top5_idx;
   if (!same) {                                            // new key: drop the old graph, run eagerly once (allocations, attributes)
@@ -921,6 +967,7 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step)));
   h->launches += launch_adam(h->n_params, h->params, h->grads, h->adam_m, h->adam_v, 1.0f / (float)(accum_steps * world), 0.2f,
                              lr_t, (float)b1, (float)b2, 1e-8f, (cudaStream_t)stream);
+  h->weights_dirty = true;
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
@@ -970,9 +1017,9 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   ConvProblem p; memset(&p, 0, sizeof(p));
   p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
-  if (precision != DR_PREC_FP32 && !reuse) { int rc = prep_weights(h, precision, (cudaStream_t)stream); if (rc) return rc; }
+  if (precision != DR_PREC_FP32 && !reuse) { int rc = ensure_prepped(h, precision, (cudaStream_t)stream); if (rc) return rc; }
   set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout; p.pair = force_pair ? 2 : 0;
-  h->launches += run_conv(h, p, precision, (cudaStream_t)stream);
+  { int64_t nl = 0; RUN_TRY(nl, run_conv(h, p, precision, (cudaStream_t)stream)); h->launches += nl; }
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
@@ -989,16 +1036,16 @@ int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const floa
     wp.x = x; wp.x_cs = L.cin; wp.dy = dy; wp.dy_cs = L.cout; wp.B = B; wp.H = L.in_hw; wp.W = L.in_hw; wp.Cin = L.cin;
     wp.Ho = L.out_hw; wp.Wo = L.out_hw; wp.Cout = L.cout; wp.k = L.k; wp.stride = L.stride;
     wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride); wp.dw = dw;
-    h->launches += run_wgrad(h, wp, precision, st);
+    { int64_t nl = 0; RUN_TRY(nl, run_wgrad(h, wp, precision, st)); h->launches += nl; }
   }
   if (dx) {
     if (L.stride != 1) return fail(h, DR_ERR_UNSUPPORTED, "dgrad only for stride-1 convs (the stem conv has no input gradient)");
-    { int rc = prep_weights(h, precision, st); if (rc) return rc; }
+    { int rc = ensure_prepped(h, precision, st); if (rc) return rc; }
     ConvProblem p; memset(&p, 0, sizeof(p));
     p.x = dy; p.x_cs = L.cout; p.B = B; p.H = L.out_hw; p.W = L.out_hw; p.Cin = L.cout; p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin;
     p.k = L.k; p.stride = 1; p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, 1);
     set_dgrad_weights(h, L, precision, p); p.y = dx; p.y_cs = L.cin;
-    h->launches += run_conv(h, p, precision, st);
+    { int64_t nl = 0; RUN_TRY(nl, run_conv(h, p, precision, st)); h->launches += nl; }
   }
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;

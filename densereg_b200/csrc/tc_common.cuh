@@ -4,6 +4,10 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace tc {
 
@@ -103,6 +107,18 @@ DR_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 
+DR_DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+DR_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // MN-major TF32 operand descriptor.  For 32-bit MN-major operands the only layout the tensor core accepts is
 // SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom: 32-float = 128 B runs along M/N, 4 k-rows per 512 B atom, 32 B chunks
 // XOR-swizzled with the row index; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  LBO = byte stride between 32-wide M/N
@@ -133,19 +149,69 @@ inline EncodeFn get_encode() {
   return fn;
 }
 
+// why the last tensor-core launch of this thread failed (run_conv / run_wgrad report it through dr_last_error; there is no FFMA fallback)
+inline char* last_error_buf() { static thread_local char buf[192] = "ok"; return buf; }
+inline const char* last_error() { return last_error_buf(); }
+inline void set_error(const char* what, int code) { snprintf(last_error_buf(), 192, "%s (code %d)", what, code); }
+
+// Tensor maps are pure functions of (base, rank, dims, strides, box, swizzle).  The arena pointers, layer shapes and batch sizes of a
+// handle repeat every micro-batch, so each map is encoded ONCE and looked up afterwards: 2-5 driver calls per tensor-core launch
+// (~600 launches per micro-batch) become hash lookups.  DENSEREG_TMAP_CACHE=0 disables the cache.
+struct MapKey {
+  const void* base; int rank; int swizzle; cuuint64_t dims[5]; cuuint64_t strides[4]; cuuint32_t box[5];
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t hsh = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { hsh ^= w[i] + 0x9E3779B97F4A7C15ull + (hsh << 6) + (hsh >> 2); }
+    return (size_t)hsh;
+  }
+};
+struct MapCache {
+  std::mutex mu;
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+  int enabled = -1;
+};
+inline MapCache& map_cache() { static MapCache c; return c; }
+
 inline bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeFn enc = get_encode();
-  if (!enc) return false;
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable", -1); return false; }
+  MapCache& mc = map_cache();
+  MapKey key; memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.swizzle = (int)swizzle;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  std::lock_guard<std::mutex> lock(mc.mu);
+  if (mc.enabled < 0) { const char* e = getenv("DENSEREG_TMAP_CACHE"); mc.enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (mc.enabled) {
+    auto it = mc.maps.find(key);
+    if (it != mc.maps.end()) { memcpy(m, &it->second, sizeof(CUtensorMap)); return true; }
+  }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    fprintf(stderr, "densereg: cuTensorMapEncodeTiled failed with CUresult %d (rank %d)\n", (int)r, rank);
+    set_error("cuTensorMapEncodeTiled failed", (int)r);
     return false;
   }
+  if (mc.enabled) {
+    if (mc.maps.size() > 65536) mc.maps.clear();            // debug entry points with ever-changing pointers must not grow it without bound
+    mc.maps.emplace(key, *m);
+  }
   return true;
+}
+
+// launch status of a tensor-core kernel: records the reason when it is not cudaSuccess
+inline bool launch_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  snprintf(last_error_buf(), 192, "%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();
+  return false;
 }
 
 

@@ -715,7 +715,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
       const size_t asmem = (size_t)a_stages * a_stage + (3 * a_stages + 4) * 8 + 16 + 1024 + 64;
       if (!aattr) { cudaFuncSetAttribute(wgrad_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); aattr = true; }
       wgrad_tc_atmem_kernel<<<dim3(total_items < num_sms_a ? total_items : num_sms_a), 192 + WG_SPLIT_THREADS, asmem, st>>>(mx, mdy, ta);
-      return 1;
+      return launch_ok(cudaPeekAtLastError(), "wgrad_tc_atmem_kernel") ? 1 : 0;
     }
   }
   if (persist) {
@@ -732,7 +732,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
       if (!pattr[0]) { cudaFuncSetAttribute(wgrad_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); pattr[0] = true; }
       wgrad_tc_persist_kernel<false><<<pgrid, 192, psmem, st>>>(mx, mdy, t);
     }
-    return 1;
+    return launch_ok(cudaPeekAtLastError(), "wgrad_tc_persist_kernel") ? 1 : 0;
   }
   dim3 grid(t.cin_tiles * p.k * p.k, cout_tiles, splits);
   if (split3) {
@@ -742,5 +742,5 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
     if (!attr_set[0]) { cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[0] = true; }
     wgrad_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(mx, mdy, t);
   }
-  return 1;
+  return launch_ok(cudaPeekAtLastError(), "wgrad_tc_kernel") ? 1 : 0;
 }

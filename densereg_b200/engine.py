@@ -23,7 +23,7 @@ def _ptr(t):
 
 
 class DenseRegEngine:
-    def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="fp32", device=0,
+    def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="tf32x3", device=0,
                  kernel_size=3, training=True, infer_graph=False, tc_pair=True):
         if not torch.cuda.is_available():
             raise DenseRegError("densereg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -97,6 +97,11 @@ class DenseRegEngine:
         self.params.copy_(params.to(self.device, torch.float32))
         if state is not None:
             self.state.copy_(state.to(self.device, torch.float32))
+        self.params_changed()
+
+    def params_changed(self):
+        """Tell the library that `self.params` was written from outside (it rebuilds its tensor-core weight copies)."""
+        self._check(self.lib.dr_params_changed(self._h))
 
     # ------------------------------------------------------------------------------------------
     def norm_dm(self, dm_mm, coms):

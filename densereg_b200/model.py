@@ -17,6 +17,7 @@ the box, so by default SyntheticDataset generates seed
 import argparse
 import os
 import time
+from datetime import datetime
 
 import numpy as np
 import torch
@@ -46,7 +47,7 @@ def build_argparser():
     p.add_argument("--num_fea", type=int, default=128)
     p.add_argument("--kernel_size", type=int, default=3)
     # additions (not in the reference): arithmetic mode and a bound on synthetic steps
-    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "tf32", "tf32x3"])
+    p.add_argument("--precision", type=str, default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
     p.add_argument("--max_steps", type=int, default=0, help="stop after this many optimiser steps (0 = epoch schedule)")
     p.add_argument("--test_num", type=int, default=0, help="number of synthetic test frames (0 = dataset's exact_num)")
     p.add_argument("--restore_step", type=int, default=None,
@@ -54,6 +55,8 @@ def build_argparser():
     p.add_argument("--data_source", type=str, default="auto", choices=["auto", "synthetic", "tfrecord"],
                    help="tfrecord = the reference's shards under --data_dir; auto = tfrecord when every shard exists, else synthetic")
     p.add_argument("--data_dir", type=str, default=None, help="dataset root (default: the reference's ./exp/data/<dataset>/)")
+    p.add_argument("--allow_random_init", type=str2bool, default=False,
+                   help="--is_train False without a checkpoint: test the freshly initialised network instead of failing like saver.restore")
     return p
 
 
@@ -257,6 +260,7 @@ def augment(engine, tens, rng):
 
 def shard_batch(batch_size, rank, world):
     """tf.split of the global minibatch across towers (train_multi_gpu.py:63-64) -> [lo, hi) of this rank."""
+    assert batch_size % world == 0, "batch_size must be divisible by the number of GPUs (train_multi_gpu.py:59)"
     per = batch_size // world
     return rank * per, (rank + 1) * per
 
@@ -277,28 +281,35 @@ def train(model, rank=0, world=1, log=print, start_step=0):
     max_steps = f.max_steps or model.max_steps
     lo, hi = shard_batch(f.batch_size, rank, world)
     dev = eng.device
-    t_log = time.time()
     rng = np.random.RandomState(1234 + rank)
     tlog = vlog = None
     if rank == 0:
         os.makedirs(model.train_dir, exist_ok=True)
         tlog = open(os.path.join(model.train_dir, "training_log.txt"), "a")
         vlog = open(os.path.join(model.train_dir, "validation_log.txt"), "a")
+    bad = None                                                                     # device-side "some loss was not finite" flag (no sync per step)
     for step in range(start_step, max_steps):                                      # resume: train_single_gpu.py:125-128
+        t_step = time.time()
         eng.zero_grads()                                                           # reset_op :139
+        ave_loss = None
         for sub in range(f.sub_batch):                                             # :140-148
             tens = list(model.train_dataset.batch_device(eng, f.batch_size, seed=step * f.sub_batch + sub, lo=lo, hi=hi)[:4])
             if f.is_aug:                                                               # hourglass_um_crop_tiny.py:333-334
                 tens[0], tens[1] = augment(eng, tens, rng)
             loss = model.loss(*tens, dropout_seed=(step * f.sub_batch + sub) * world + rank)
+            ave_loss = loss.clone() if ave_loss is None else ave_loss + loss           # ave_loss += loss_value :147 (device add, no sync)
+            nf = ~torch.isfinite(loss[0])
+            bad = nf if bad is None else (bad | nf)
         allreduce_gradients(eng.grads, world)
         eng.optimizer_step(step + 1, model.lr_at(step), accum_steps=f.sub_batch, world=world)   # train_op :150
+        if step % 5 == 0 or step + 1 == max_steps:                                 # every rank checks its own micro-batches (:146), one sync per 5 steps
+            assert not bool(bad), "Model diverged with loss = NaN (rank %d, step <= %d)" % (rank, step)
         if step % 5 == 0 and rank == 0:                                            # :154-158
-            lv = loss.cpu().numpy()
-            assert not np.isnan(lv[0]), "Model diverged with loss = NaN"         # :147
-            dt = time.time() - t_log; t_log = time.time()
-            msg = ("step %d, loss = %.2f (hm %.2f hm3 %.2f um %.2f reg %.3f) lr %.1e, %.3f sec/5 steps"
-                   % (step, lv[0], lv[1], lv[2], lv[3], lv[4], model.lr_at(step), dt))
+            lv = (ave_loss / f.sub_batch).cpu().numpy()
+            duration = time.time() - t_step
+            msg = ("[model/train_multi_gpu] %s: step %d/%d, loss = %.3f, %.3f sec/batch, %.3f sec/sample"    # the reference's format string :155
+                   % (datetime.now(), step, max_steps, lv[0], duration, duration / (f.batch_size * f.sub_batch)))
+            msg += " (hm %.2f hm3 %.2f um %.2f reg %.3f, lr %.1e)" % (lv[1], lv[2], lv[3], lv[4], model.lr_at(step))
             log(msg); tlog.write(msg + "\n"); tlog.flush()
         if step % 40 == 0 and rank == 0 and model.is_validate:                     # do_test every 40 steps :165-166
             try:                                                                   # batch of 3 like the reference (:62-65)
@@ -308,8 +319,9 @@ def train(model, rank=0, world=1, log=print, start_step=0):
             xyz = model.test(vd, vc, vm).cpu().numpy()
             err = [meanJntError(x, g) for x, g in zip(xyz, vp.cpu().numpy())]
             vlog.write("step %d mean joint error (mm): %s\n" % (step, " ".join("%.3f" % e for e in err))); vlog.flush()
-        if (step + 1) % 100 == 0 and rank == 0:                                    # :168-175
+        if ((step + 1) % 100 == 0 or step + 1 == max_steps) and rank == 0:         # :168-175 (every 100 steps AND after the last one)
             model.save(step + 1)
+            tlog.write("model has been saved to %s\n" % os.path.join(model.train_dir, "model.ckpt")); tlog.flush()
     if rank == 0:
         tlog.close(); vlog.close()
     return max_steps
@@ -368,6 +380,8 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if flags.is_train and flags.batch_size % world != 0:
+        raise SystemExit("--batch_size %d is not divisible by the %d GPUs (train_multi_gpu.py:59)" % (flags.batch_size, world))
     ds, val = open_datasets(flags)
     model = JointDetectionModel(ds, flags, val_dataset=val, device=local, world=world)
     model.engine.init_params(seed=0)
@@ -379,7 +393,10 @@ def main(argv=None):
     elif flags.restore_step is not None:
         raise FileNotFoundError("no checkpoint %s/model.ckpt-%d(.index|.pt)" % (model.train_dir, step))
     elif not flags.is_train:
-        print("[densereg_b200] no checkpoint %s/model.ckpt--1 -- testing the freshly initialised network" % model.train_dir)
+        if not flags.allow_random_init:                        # saver.restore would fail here (test_model.py:31-35)
+            raise FileNotFoundError("no checkpoint %s/model.ckpt-%d(.index|.pt); pass --allow_random_init True to test an untrained network"
+                                    % (model.train_dir, step))
+        print("[densereg_b200] no checkpoint %s/model.ckpt-%d -- testing the freshly initialised network (--allow_random_init)" % (model.train_dir, step))
     if flags.is_train:
         train(model, rank, world, start_step=max(start_step, 0))
     else:

@@ -91,6 +91,11 @@ DR_API int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out);
  * model/train_single_gpu.py:108).  grads/adam_m/adam_v may be NULL for inference-only use. */
 DR_API int dr_bind(dr_handle* h, float* params, float* state, float* grads, float* adam_m, float* adam_v);
 
+/* The caller wrote into the bound `params` buffer itself (checkpoint restore = saver.restore, model/test_model.py:31-35): the
+ * library rebuilds its tensor-core weight copies on the next forward.  dr_init_params / dr_optimizer_step / dr_bind do this
+ * implicitly. */
+DR_API int dr_params_changed(dr_handle* h);
+
 /* ops.py:272 truncated_normal(stddev), ops.py:86-128 BRN initial values.  Needs dr_bind first. */
 DR_API int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream);
 

@@ -88,10 +88,15 @@ def test_train_loop_sharding_logs_and_checkpoints(fake, monkeypatch):
     assert not os.path.exists(model.train_dir) and logs == []             # only rank 0 logs / saves
     # rank 0, single process: logs every 5 steps, validation every 40, checkpoint at step 100 in BOTH formats
     M.train(model, rank=0, world=1, log=logs.append)
-    assert len(logs) == 21 and logs[0].startswith("step 0, loss = 10.00 (hm 1.00 hm3 2.00 um 3.00 reg 0.500) lr 1.0e-03")
+    import re
+    # the reference's format string (train_single_gpu.py:155) with the MEAN loss over the sub_batch micro-batches
+    assert len(logs) == 21 and re.match(r"\[model/train_multi_gpu\] .*: step 0/101, loss = 10\.000, \d+\.\d{3} sec/batch, \d+\.\d{3} sec/sample "
+                                        r"\(hm 1\.00 hm3 2\.00 um 3\.00 reg 0\.500, lr 1\.0e-03\)$", logs[0]), logs[0]
     tl = open(os.path.join(model.train_dir, "training_log.txt")).read().splitlines()
     vl = open(os.path.join(model.train_dir, "validation_log.txt")).read().splitlines()
-    assert len(tl) == 21 and len(vl) == 3 and vl[1].startswith("step 40 mean joint error (mm):") and len(vl[1].split(":")[1].split()) == 3
+    assert len([l for l in tl if l.startswith("[model")]) == 21 and len([l for l in tl if l.startswith("model has been saved")]) == 2 and len(vl) == 3
+    # checkpoints every 100 steps AND after the last step (train_single_gpu.py:168)
+    assert os.path.exists(os.path.join(model.train_dir, "model.ckpt-101.pt")) and vl[1].startswith("step 40 mean joint error (mm):") and len(vl[1].split(":")[1].split()) == 3
     assert os.path.exists(os.path.join(model.train_dir, "model.ckpt-100.pt")) and os.path.exists(os.path.join(model.train_dir, "model.ckpt-100.index"))
     tensors = T.read_bundle(os.path.join(model.train_dir, "model.ckpt-100"))
     assert float(tensors["global_step"]) == 100.0 and tensors["hg_imgproc/Conv/weights"].shape == (7, 7, 1, 32)
@@ -136,3 +141,20 @@ def test_main_restores_reference_checkpoint_for_testing(fake, capsys):
     with pytest.raises(FileNotFoundError):
         M.main(["--dataset", "icvl", "--num_stack", "1", "--num_fea", "64", "--batch_size", "4", "--data_source", "synthetic", "--is_train", "False",
                 "--test_num", "4", "--restore_step", "123"])
+
+
+def test_short_run_saves_final_checkpoint_and_untrained_test_needs_opt_in(fake):
+    """a run shorter than 100 steps still leaves a checkpoint (train_single_gpu.py:168 saves after the last step), and
+    `--is_train False` without any checkpoint fails like saver.restore unless --allow_random_init is given."""
+    flags = _flags("--max_steps", "7", "--is_aug", "False")
+    ds, val = M.open_datasets(flags, log=lambda *_: None)
+    model = M.JointDetectionModel(ds, flags, val_dataset=val)
+    M.train(model, rank=0, world=1, log=lambda *_: None)
+    assert model.has_checkpoint(7) and not model.has_checkpoint(100)
+    base = ["--dataset", "icvl", "--num_stack", "1", "--num_fea", "64", "--batch_size", "4", "--data_source", "synthetic", "--is_train", "False",
+            "--test_num", "4", "--is_aug", "True"]                          # another model directory (…_daug): no checkpoint there
+    with pytest.raises(FileNotFoundError):
+        M.main(base)
+    M.main(base + ["--allow_random_init", "True"])
+    with pytest.raises(AssertionError):
+        M.shard_batch(10, 0, 4)                                              # train_multi_gpu.py:59

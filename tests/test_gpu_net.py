@@ -10,6 +10,12 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+# Absolute end-to-end bars on the joint positions (mm).  fp32 = FFMA parity mode.  tf32x3 = the tensor-core path bench.py times; its bar
+# is the same 1e-3 mm when the two-level accumulation is on (the library default, DENSEREG_TC_CHUNK), 2e-2 mm otherwise (one-level
+# accumulation inside the tensor core truncates: measured 8.6e-3 mm, "throughput mode").
+XYZ_BAR_MM = {"fp32": 1e-3, "tf32x3": 2e-2 if os.environ.get("DENSEREG_TC_CHUNK", "") == "0" else 1e-3}
+
+
 def make(S, F, J, B, seed, stddev, training=True, precision="fp32"):
     from densereg_b200.engine import DenseRegEngine
     from densereg_b200 import synth
@@ -116,7 +122,8 @@ def test_infer_end_to_end(built_lib, S, F, J, B, precision):
                                                      mean_joint_err_mm=float(np.nanmean(np.linalg.norm((xyz - ref_xyz).reshape(B, J, 3), axis=-1)))))
     assert same[safe].all()
     fin = np.isfinite(err) & same
-    assert (err[fin] <= 1e-3 * max(1.0, float(np.abs(ref_xyz[np.isfinite(ref_xyz)]).max()) / 100.0)).all()
+    # ABSOLUTE bar in mm (north_star: "joint xyz within 1e-3 mm"), per arithmetic mode -- see XYZ_BAR_MM
+    assert (err[fin] <= XYZ_BAR_MM[precision]).all(), float(err[fin].max())
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
@@ -183,6 +190,75 @@ def test_training_step_matches_oracle(built_lib, S, F, J, B, precision):
     assert rep["state"] < 1e-4, rep
     # clip makes the first Adam step +-lr for almost all weights; differences only where g is ~0
     assert rep["adam_max_abs"] <= 2.1e-3, rep
+
+
+@pytest.mark.parametrize("S,F,J,B", [(2, 128, 16, 40), (2, 128, 14, 8), (2, 128, 21, 4)])
+def test_training_step_bench_shapes(built_lib, S, F, J, B):
+    """The arithmetic bench.py times (3xTF32 tensor cores, CTA-pair kernel on its real shapes at B=40) and the NYU / MSRA joint counts of
+    BASELINE.json configs 3 and 4, against the fp32 oracle: forward maps, loss, every gradient, BRN state."""
+    from oracle import um_v1_torch as U
+    eng, net, p, s, (dms, poses, cfgs, coms) = make(S, F, J, B, 17, 0.05, training=True, precision="tf32x3")
+    s_ref = s.clone()
+    L, g_ref, outs = U.loss_and_grads(net, p, s_ref, dms[..., 0], poses, cfgs, coms, dropout_seed=9)
+    out = eng.forward(cu(dms), cu(coms), is_training=True, update_state=False, dropout_seed=9)
+    rep = {"fwd_um_last": relerr(out["um_outs"][-1].cpu().numpy(), outs[2][-1].detach().numpy()),
+           "fwd_hm_last": relerr(out["hm_outs"][-1].cpu().numpy(), outs[0][-1].detach().numpy()),
+           "fwd_hm3_last": relerr(out["hm3_outs"][-1].cpu().numpy(), outs[1][-1].detach().numpy())}
+    eng.zero_grads()
+    loss = eng.loss_backward(cu(dms), cu(poses), cu(cfgs), cu(coms), dropout_seed=9, update_state=True).cpu().numpy()
+    ref_loss = np.array([L["total"], L["hm"], L["hm3"], L["um"], L["reg"]])
+    rep["loss"] = float(np.abs(loss - ref_loss).max() / np.abs(ref_loss).max())
+    g = eng.grads.cpu().numpy(); gr = g_ref.numpy()
+    per = {}
+    for c in net.specs:
+        n = c.k * c.k * c.cin * c.cout
+        per[c.name] = float(np.linalg.norm(g[c.w_off:c.w_off + n] - gr[c.w_off:c.w_off + n]) / (np.linalg.norm(gr[c.w_off:c.w_off + n]) + 1e-20))
+    rep["grad_worst"] = max(per.values()); rep["grad_worst_name"] = max(per, key=per.get)
+    rep["grad_total"] = float(np.linalg.norm(g - gr) / np.linalg.norm(gr))
+    rep["state"] = relerr(eng.state.cpu().numpy(), s_ref.numpy())
+    rep["tc_launches"] = eng.tc_launch_count
+    dump("train_bench_shapes_S%dF%dJ%dB%d.json" % (S, F, J, B), dict(rep, per_layer=per))
+    assert rep["fwd_um_last"] < 2e-4 and rep["fwd_hm_last"] < 2e-4 and rep["fwd_hm3_last"] < 2e-4, rep
+    assert rep["loss"] < 1e-4, rep
+    assert per["s%d/um_out" % (S - 1)] < 1e-4, rep
+    assert rep["grad_total"] < 2e-2 and rep["grad_worst"] < 5e-2, rep      # fp32 noise floor of this graph is ~3e-3 (see above)
+    assert rep["state"] < 1e-4, rep
+    assert eng.tc_launch_count > 0
+
+
+def test_adam_three_steps_match_oracle(built_lib):
+    """dr_optimizer_step vs oracle adam_step (train_single_gpu.py:84-88, hourglass_um_crop_tiny.py:436-439; tf.train.AdamOptimizer) over THREE
+    steps with synthetic gradients: from step 2 on the update depends on beta1, beta2 and the bias correction lr_t (step 1 alone is
+    +-lr*sign(g) whatever they are), and gradients straddle the +-0.2 clip after the 1/(accum*world) mean."""
+    from densereg_b200.engine import DenseRegEngine
+    from oracle import um_v1_torch as U
+    eng = DenseRegEngine(1, 64, 16, max_batch=1, training=True, precision="fp32")
+    n = eng.n_params
+    gen = torch.Generator().manual_seed(123)
+    p_ref = (torch.randn(n, generator=gen) * 0.01).float()
+    m = torch.zeros(n); v = torch.zeros(n)
+    eng.load_flat(p_ref.clone())
+    accum, world, lr = 5, 2, 1e-3
+    worst = 0.0
+    for step in (1, 2, 3):
+        scale = torch.tensor([1e-4, 1e-2, 1.0, 10.0])[torch.randint(0, 4, (n,), generator=gen)]
+        gsum = (torch.randn(n, generator=gen) * scale).float() * (accum * world) * 0.15       # |mean grad| from 1e-5 to > clip
+        eng.grads.copy_(gsum)
+        eng.optimizer_step(step=step, lr=lr, accum_steps=accum, world=world)
+        U.adam_step(p_ref, gsum.clone(), m, v, step=step, lr=lr, accum_steps=accum, world=world)
+        torch.cuda.synchronize()
+        dp = float((eng.params.cpu() - p_ref).abs().max())
+        dm = float((eng.adam_m.cpu() - m).abs().max() / m.abs().max())
+        dv = float((eng.adam_v.cpu() - v).abs().max() / v.abs().max())
+        worst = max(worst, dp)
+        assert dp <= 1e-7 and dm <= 1e-6 and dv <= 1e-6, (step, dp, dm, dv)
+    # the test discriminates: a wrong beta2 or a missing bias correction moves the parameters by far more than the bar
+    p_bad = p_ref.clone(); m2 = m.clone(); v2 = v.clone()
+    U.adam_step(p_bad, gsum.clone(), m2, v2, step=3, lr=lr, accum_steps=accum, world=world, beta2=0.99)
+    p_ok = p_ref.clone(); m3 = m.clone(); v3 = v.clone()
+    U.adam_step(p_ok, gsum.clone(), m3, v3, step=3, lr=lr, accum_steps=accum, world=world)
+    assert float((p_bad - p_ok).abs().max()) > 1e-5
+    dump("adam_three_steps.json", {"max_abs_param_diff": worst})
 
 
 def test_grad_accumulation_equals_rank_sum(built_lib):
