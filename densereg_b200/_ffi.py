@@ -24,6 +24,11 @@ class DrLayerInfo(C.Structure):
                 ("in_hw", C.c_int32), ("out_hw", C.c_int32)]
 
 
+class DrTraceRec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("B", C.c_int32), ("hw", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
+                ("kernel", C.c_int32), ("ms", C.c_float)]
+
+
 # every symbol include/densereg.h declares: name -> (restype, argtypes)
 _P, _F, _I32P = C.c_void_p, C.c_void_p, C.c_void_p
 SIGNATURES = {
@@ -44,6 +49,10 @@ SIGNATURES = {
     "dr_vote": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _F, _F, _F, _F, _F, _F, _F, _I32P, _I32P, _P]),
     "dr_infer": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _I32P, _P]),
     "dr_loss_backward": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _F, C.c_uint64, C.c_int, _P]),
+    "dr_comm_unique_id": (C.c_int, [_P]),
+    "dr_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "dr_comm_overlap_next_backward": (C.c_int, [_P]),
+    "dr_comm_allreduce_count": (C.c_int64, [_P]),
     "dr_zero_grads": (C.c_int, [_P, _P]),
     "dr_optimizer_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int64, _P]),
     "dr_crop_from_xyz_pose": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _F, _F, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float,
@@ -53,6 +62,9 @@ SIGNATURES = {
     "dr_debug_conv": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, C.c_int, _P]),
     "dr_debug_conv_bwd": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, C.c_int, _P]),
     "dr_debug_get_output": (C.c_int, [_P, C.c_int, C.c_int, _F, C.c_int, _P]),
+    "dr_trace": (C.c_int, [_P, C.c_int]),
+    "dr_trace_count": (C.c_int, [_P]),
+    "dr_trace_get": (C.c_int, [_P, C.c_int, C.POINTER(DrTraceRec)]),
     "dr_launch_count": (C.c_int64, [_P]),
     "dr_tc_launch_count": (C.c_int64, [_P]),
     "dr_workspace_bytes": (C.c_size_t, [_P]),

@@ -99,10 +99,6 @@ int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const flo
 // backward reductions: g = dy*(z>0); sums[0:C]=sum g, sums[C:2C]=sum g*xhat   (z = raw*a+b, xhat=(raw-mean)*inv_std)
 int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st);
-// fused cooperative version of the two kernels below (returns 0 if not applicable); counter must be zero on entry
-int launch_brn_bwd_fused(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs, const float* aff, const float* bstat,
-                         const float* beta_gamma, int relu, double* sums, unsigned int* counter, float* draw, int draw_cs, float* gparam,
-                         cudaStream_t st);
 // draw = gamma*r*inv_std*(g - sum_g/N - xhat*sum_gx/N); also dbeta,dgamma accumulated into gparam
 int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                          const float* aff, const float* bstat, const float* beta_gamma, int relu,
@@ -122,8 +118,9 @@ struct LossArgs {
 int launch_loss(const LossArgs& a, cudaStream_t st);
 int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, double* reg_acc, cudaStream_t st);
 int launch_finish_loss(const double* acc /*hm,hm3,um,reg*/, float* out5, cudaStream_t st);
-int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
-                float lr_t, float b1, float b2, float eps, cudaStream_t st);
+// g / divisor, clip, TF ApplyAdam: alpha = lr*sqrt(1-b2^t)/(1-b1^t) (fp32), omb = 1.0f - beta
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float divisor, float clip,
+                float alpha, float omb1, float omb2, float eps, cudaStream_t st);
 int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st);
 int launch_gather_outputs(size_t npix, int C, const float* src, int src_cs, float* dst, cudaStream_t st);
 

@@ -27,7 +27,6 @@ struct TcParams {
   const float* res; int res_cs; int accumulate;
   int dropout; unsigned long long drop_seed; unsigned int drop_tag;
   double* stats; unsigned int* stats_counter; const float* bn_bg; float* bn_state; float* bn_aff; float* bn_bstat; int bn_update_state;
-  int full_items, tail_f;  // pair kernel: items >= full_items are 1/tail_f-wide N slices of the last wave's items (tail_f = 1: off)
   int stats_per_cta;     // fused BRN statistics: accumulate per CTA in shared memory, ONE round of atomics + fence + counter per CTA (opt-in)
   int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
   int chunk_kb;          // > 0: two-level accumulation -- the tensor core sums at most chunk_kb k-blocks into a partial accumulator (its fp32 adds
@@ -74,7 +73,7 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     float* yr = p.y + (size_t)m * p.y_cs;
     const float* rr = p.res ? p.res + (size_t)m * p.res_cs : nullptr;
     const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
-    for (int cb = 0; cb < bn; cb += 32) {          // bn = columns of this work item (p.BN, or a slice of it in the pair kernel's tail)
+    for (int cb = 0; cb < bn; cb += 32) {          // bn = columns of this work item (p.BN)
       uint32_t v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
       if (has2) {

@@ -67,8 +67,7 @@ DR_DEVINL void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
 // Work item = (pixel-tile PAIR, n-tile); cluster c walks items c, c + #clusters, ...; CTA rank r owns pixel tile 2*pair + r.
 __global__ void __launch_bounds__(192 + SPLIT_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_wt,
-                    const __grid_constant__ CUtensorMap map_wlot, TcParams p) {
+                    const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bh_bytes = (p.BN / 2) * TC_BK * 4;                   // this CTA's half of one weight tile (hi or lo)
@@ -84,21 +83,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int pairs_m = (p.tiles_m + 1) >> 1;
-  const int base_items = pairs_m * p.tiles_n;
-  // Tail splitting (p.tail_f > 1): the items of the last, partly filled wave (index >= p.full_items) are cut into tail_f slices along N so that
-  // they spread over all clusters instead of leaving most SMs idle for a whole item time (160 items on 74 clusters = 2.16 waves otherwise cost 3).
-  const int total_items = p.full_items + (base_items - p.full_items) * p.tail_f;
+  const int total_items = pairs_m * p.tiles_n;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   struct PItem { int pair, n0, bn; };
   auto decode = [&](int item) {
     PItem w;
-    if (item < p.full_items) {
-      w.pair = item / p.tiles_n; w.n0 = (item - w.pair * p.tiles_n) * p.BN; w.bn = p.BN;
-    } else {
-      const int tq = item - p.full_items, whole = tq / p.tail_f, sub = tq - whole * p.tail_f, base = p.full_items + whole;
-      w.bn = p.BN / p.tail_f;
-      w.pair = base / p.tiles_n; w.n0 = (base - w.pair * p.tiles_n) * p.BN + sub * w.bn;
-    }
+    w.pair = item / p.tiles_n; w.n0 = (item - w.pair * p.tiles_n) * p.BN; w.bn = p.BN;
     return w;
   };
 
@@ -125,7 +115,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t it = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters) {
         const PItem w = decode(item);
-        const bool sliced = w.bn != p.BN;
         const uint32_t tx = (uint32_t)(A_TILE_BYTES + 2 * (w.bn / 2) * TC_BK * 4);
         const int pix0 = (w.pair * 2 + (int)rank) * TC_BM;        // may lie past M for the odd tail: TMA zero-fills, the epilogue masks
         const int img = pix0 / (p.H * p.W);
@@ -143,8 +132,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tma_load_4d(&map_a, &full_bar[s], st, c0, dx, y0 + dy, img);
           uint8_t* bdst = st + 2 * A_TILE_BYTES;
           const int wtap = p.flip_taps ? p.ksz * p.ksz - 1 - tap : tap;
-          tma_load_3d(sliced ? &map_wt : &map_w, &full_bar[s], bdst, c0, nb0, wtap);                   // lo stays at the full-size offset
-          tma_load_3d(sliced ? &map_wlot : &map_wlo, &full_bar[s], bdst + bh_bytes, c0, nb0, wtap);
+          tma_load_3d(&map_w, &full_bar[s], bdst, c0, nb0, wtap);
+          tma_load_3d(&map_wlo, &full_bar[s], bdst + bh_bytes, c0, nb0, wtap);
         }
       }
     }
@@ -290,11 +279,11 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   t.stats = p.stats; t.stats_counter = p.stats_counter; t.bn_bg = p.bn_bg; t.bn_state = p.bn_state; t.bn_aff = p.bn_aff; t.bn_bstat = p.bn_bstat;
   t.bn_update_state = p.bn_update_state;
   { static int co = -1; if (co < 0) { const char* e = getenv("DENSEREG_TC_EPI_COALESCE"); co = (e && e[0] == '0') ? 0 : 1; } t.coalesce = co; }
-  { static int pc = -1; if (pc < 0) { const char* e = getenv("DENSEREG_TC_STATS_PER_CTA"); pc = (e && e[0] == '1') ? 1 : 0; }
+  { static int pc = -1; if (pc < 0) { const char* e = getenv("DENSEREG_TC_STATS_PER_CTA"); pc = (e && e[0] == '0') ? 0 : 1; }   // default on: measured -0.12 ms per micro-batch (profiles/r2_sweep.md)
     t.stats_per_cta = (pc && p.stats && !p.scale && !p.shift) ? 1 : 0; }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;
 
-  CUtensorMap ma, mw, mwlo, mwt, mwlot;
+  CUtensorMap ma, mw, mwlo;
   const int rows = TC_BM / p.W;
   const int bh = rows < p.H ? rows : p.H;
   const int bb = rows < p.H ? 1 : rows / p.H;
@@ -312,22 +301,6 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
   const int items = ((t.tiles_m + 1) / 2) * t.tiles_n;
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
-  // tail splitting (opt-in, DENSEREG_TC_PAIR_TAIL=1): slice the last wave's r items by the largest power of two f with f*r <= clusters
-  t.full_items = items; t.tail_f = 1;
-  mwt = mw; mwlot = mwlo;
-  {
-    static int tail = -1;
-    if (tail < 0) { const char* e = getenv("DENSEREG_TC_PAIR_TAIL"); tail = (e && e[0] == '1') ? 1 : 0; }
-    const int r = items % clusters;
-    if (tail && items > clusters && r > 0 && 2 * r <= clusters) {
-      int f = 2;
-      while (2 * f * r <= clusters && f < 8 && (BN / (2 * f)) % 16 == 0 && BN / (2 * f) >= 32) f *= 2;
-      if ((BN / f) % 16 == 0 && BN / f >= 32) {
-        cuuint32_t wbt[3] = {(cuuint32_t)TC_BK, (cuuint32_t)(BN / f / 2), 1};
-        if (tc::encode_map(&mwt, p.w_kmajor, 3, wd, ws, wbt) && tc::encode_map(&mwlot, p.w_kmajor_lo, 3, wd, ws, wbt)) { t.tail_f = f; t.full_items = items - r; }
-      }
-    }
-  }
   if (!attr_set) {
     if (!tc::launch_ok(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536), "conv_tc_pair_kernel smem attribute")) return 0;
     attr_set = true;
@@ -338,5 +311,5 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return tc::launch_ok(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, mwt, mwlot, t), "conv_tc_pair_kernel") ? 1 : 0;
+  return tc::launch_ok(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, t), "conv_tc_pair_kernel") ? 1 : 0;
 }

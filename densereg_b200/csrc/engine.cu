@@ -8,6 +8,7 @@
 // tracker deciding overwrite-vs-accumulate for every gradient write.
 #include "../../include/densereg.h"
 #include "common.cuh"
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -95,6 +96,19 @@ struct dr_handle {
                       cudaGraphExec_t exec = nullptr; int warm = 0; };
   InferGraph infer_graph;
   cudaStream_t capture_stream = nullptr;
+  // in-library data-parallel communicator (dr_comm_init): ONE NCCL all-reduce(sum) of the flat gradient per optimiser step, issued in
+  // buckets on `comm_stream` while the backward pass of the step's LAST micro-batch is still running (dr_comm_overlap_next_backward)
+  void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bucket_main = nullptr, ev_bucket_side = nullptr, ev_comm_done = nullptr;
+  struct Bucket { int64_t lo, hi; int first_op; };       // flat range [lo,hi) is final once the reverse walk has finished op `first_op`
+  std::vector<Bucket> buckets;
+  bool overlap_armed = false, reduced_in_backward = false;
+  int64_t allreduce_calls = 0;
+  // per-launch timing of the conv-type kernels (dr_trace): bench.py's per-class roofline
+  bool trace_on = false;
+  std::vector<dr_trace_rec> trace;
+  float b1p = 1.0f, b2p = 1.0f; int64_t pow_step = 0;      // Adam beta powers (fp32, advanced once per step like TF's variables)
 };
 
 namespace {
@@ -380,23 +394,31 @@ struct Exec {
   View whole(int buf) const { View v; v.buf = buf; v.coff = 0; v.C = h->bufs[buf].C; return v; }
 };
 
-// DENSEREG_TRACE=1: every conv / wgrad launch is timed on its own (events + sync, so launches are serialised) and reported on stderr as
+// DENSEREG_TRACE=1 or dr_trace(h, 1): every conv / wgrad launch is timed on its own (events + sync, so launches are serialised) and reported on stderr as
 //   TRACE <conv|dgrad|wgrad> B H Cin Cout k <kernel: tc|pair|simt> <ms>      -- the per-layer time table of a step (tools/layer_times.py)
-static bool trace_on() {
+static bool trace_env() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("DENSEREG_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
   return on == 1;
 }
 struct TraceScope {
-  cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t st; bool on;
-  explicit TraceScope(cudaStream_t s) : st(s), on(trace_on()) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t st; bool on; dr_handle* h;
+  TraceScope(dr_handle* hh, cudaStream_t s) : st(s), on(trace_env() || hh->trace_on), h(hh) {
     if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   }
   void done(const char* what, int B, int H, int Cin, int Cout, int k, const char* kern) {
     if (!on) return;
     cudaEventRecord(e1, st); cudaEventSynchronize(e1);
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
-    fprintf(stderr, "TRACE %s %d %d %d %d %d %s %.4f\n", what, B, H, Cin, Cout, k, kern, ms);
+    if (trace_env()) fprintf(stderr, "TRACE %s %d %d %d %d %d %s %.4f\n", what, B, H, Cin, Cout, k, kern, ms);
+    if (h->trace_on) {
+      dr_trace_rec r; memset(&r, 0, sizeof(r));
+      r.kind = what[0] == 'c' ? 0 : (what[0] == 'd' ? 1 : 2);
+      r.B = B; r.hw = H; r.cin = Cin; r.cout = Cout; r.k = k;
+      r.kernel = kern[0] == 's' ? 0 : (kern[0] == 't' ? 1 : 2);
+      r.ms = ms;
+      h->trace.push_back(r);
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
 };
@@ -404,7 +426,7 @@ struct TraceScope {
 // A problem the tensor-core path accepts (conv_tc_eligible / wgrad_tc_eligible) MUST run there: a failed tensor-map encode or launch is an
 // error (negative return, message in dr_last_error), never a quiet switch to the FFMA kernels.
 int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st) {
-  TraceScope tr(st);
+  TraceScope tr(h, st);
   if (precision != DR_PREC_FP32 && conv_tc_eligible(p)) {
     ConvProblem q = p;
     q.pair = p.pair ? p.pair : (h->tc_pair ? 1 : 0);
@@ -424,7 +446,7 @@ int run_conv(dr_handle* h, const ConvProblem& p, int precision, cudaStream_t st)
 }
 
 int run_wgrad(dr_handle* h, const WgradProblem& p, int precision, cudaStream_t st) {
-  TraceScope tr(st);
+  TraceScope tr(h, st);
   if (precision != DR_PREC_FP32 && wgrad_tc_eligible(p)) {
     int n = launch_wgrad_tc(p, precision == DR_PREC_TF32X3, st);
     if (n <= 0) {
@@ -604,6 +626,8 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
   return DR_OK;
 }
 
+int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st);   // NCCL all-reduce of grads[lo,hi) (defined with the communicator below)
+
 int apply_fills(dr_handle* h, Exec& X, const GradWrite& g, cudaStream_t st) {
   int nl = 0;
   for (int i = 0; i < g.nfill; ++i) nl += launch_fill_view(X.npix(g.fill[i]), g.fill[i].C, X.gptr(g.fill[i]), X.cs(g.fill[i]), 0.f, st);
@@ -616,7 +640,6 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   int nl = 0;
   const int OUT = h->cfg.out_hw, J = h->cfg.num_jnt, S = h->cfg.num_stack;
   CUDA_TRY(h, cudaMemsetAsync(h->sums_bw, 0, h->n_sums * sizeof(double), st));
-  CUDA_TRY(h, cudaMemsetAsync(h->counters_bw, 0, h->layers.size() * sizeof(unsigned int), st));
   CUDA_TRY(h, cudaMemsetAsync(h->loss_acc, 0, 4 * sizeof(double), st));
   // loss + dL/d(outputs)
   LossArgs la; memset(&la, 0, sizeof(la));
@@ -632,8 +655,18 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
 
   int conv_idx = 0;
+  const bool overlap = h->overlap_armed && h->nccl_comm && h->comm_world > 1;
+  size_t next_bucket = 0;
+  h->overlap_armed = false;
   for (int oi = (int)h->ops.size() - 1; oi >= 0; --oi) {
     const Op& o = h->ops[oi];
+    if (overlap) {           // every bucket whose last contributing op (in this reverse walk) lies behind us is final: reduce it now
+      while (next_bucket < h->buckets.size() && h->buckets[next_bucket].first_op > oi) {
+        int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st);
+        if (rc) return rc;
+        ++next_bucket;
+      }
+    }
     switch (o.kind) {
       case OP_CONV: {
         const Layer& L = h->layers[o.layer];
@@ -649,14 +682,9 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         if (L.brn) {
           View rv = X.whole(o.raw);
           double* sums = h->sums_bw + L.sum_off;
-          int nf = launch_brn_bwd_fused(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
-                                        h->params + L.p_off, L.relu, sums, h->counters_bw + o.layer, dz, dz_cs, h->grads + L.p_off, st);
-          if (nf == 0) {
-            nf += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
-            nf += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
-                                       h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
-          }
-          nl += nf;
+          nl += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
+          nl += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
+                                     h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
         } else {
           nl += launch_bias_bwd(np, L.cout, dy, dy_cs, X.ptr(o.out), X.cs(o.out), L.relu, o.dropout_tag >= 0, dz, dz_cs, h->grads + L.p_off, st);
         }
@@ -707,12 +735,102 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         break;
     }
   }
+  if (overlap) {
+    while (next_bucket < h->buckets.size()) {
+      int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st);
+      if (rc) return rc;
+      ++next_bucket;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_comm_done, h->comm_stream));
+    h->reduced_in_backward = true;
+  }
   if (h->side_stream) {          // the optimiser step / next micro-batch on `st` must see every filter gradient
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->wgrad_stream));
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   h->launches += nl;
   CUDA_TRY(h, cudaGetLastError());
+  return DR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL (resolved at run time: the library neither links libnccl nor needs it unless dr_comm_init is called; inside a PyTorch
+// process the already loaded libnccl.so.2 is reused)
+// ---------------------------------------------------------------------------------------------
+struct DrNcclId { char internal[128]; };                   // == ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES 128)
+struct NcclApi {
+  typedef int (*GetUniqueId_t)(void*);
+  typedef int (*CommInitRank_t)(void**, int, DrNcclId, int);
+  typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef int (*CommDestroy_t)(void*);
+  typedef const char* (*GetErrorString_t)(int);
+  void* lib = nullptr;
+  int (*get_unique_id)(void*) = nullptr;
+  void* comm_init_rank = nullptr;
+  AllReduce_t all_reduce = nullptr;
+  CommDestroy_t comm_destroy = nullptr;
+  GetErrorString_t error_string = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!a.lib) a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) {
+      a.get_unique_id = reinterpret_cast<int (*)(void*)>(dlsym(a.lib, "ncclGetUniqueId"));
+      a.comm_init_rank = dlsym(a.lib, "ncclCommInitRank");
+      a.all_reduce = reinterpret_cast<NcclApi::AllReduce_t>(dlsym(a.lib, "ncclAllReduce"));
+      a.comm_destroy = reinterpret_cast<NcclApi::CommDestroy_t>(dlsym(a.lib, "ncclCommDestroy"));
+      a.error_string = reinterpret_cast<NcclApi::GetErrorString_t>(dlsym(a.lib, "ncclGetErrorString"));
+      a.ok = a.get_unique_id && a.comm_init_rank && a.all_reduce && a.comm_destroy;
+    }
+  }
+  return a;
+}
+int nccl_fail(dr_handle* h, const char* what, int code) {
+  NcclApi& a = nccl_api();
+  h->err = std::string(what) + ": " + (a.error_string ? a.error_string(code) : "NCCL error") + " (" + std::to_string(code) + ")";
+  return DR_ERR_CUDA;
+}
+
+// gradient buckets for the overlapped all-reduce: ~equal parameter counts, cut at layer boundaries, last layers first (their gradients
+// are final first in the reverse walk).  A bucket is final once the walk has finished the EARLIEST (forward order) conv op among its layers.
+void plan_buckets(dr_handle* h, int nbuckets) {
+  h->buckets.clear();
+  const int nl = (int)h->layers.size();
+  std::vector<int> op_of_layer(nl, 0);
+  for (int oi = 0; oi < (int)h->ops.size(); ++oi)
+    if (h->ops[oi].kind == OP_CONV) op_of_layer[h->ops[oi].layer] = oi;
+  const int64_t per = ((int64_t)h->n_params + nbuckets - 1) / nbuckets;
+  int hi_layer = nl;                                         // exclusive
+  while (hi_layer > 0) {
+    const int64_t hi_off = hi_layer == nl ? (int64_t)h->n_params : h->layers[hi_layer].w_off;
+    int lo_layer = hi_layer - 1;
+    while (lo_layer > 0 && hi_off - h->layers[lo_layer].w_off < per) --lo_layer;
+    if ((int)h->buckets.size() == nbuckets - 1) lo_layer = 0;  // the last bucket takes everything that is left
+    int first_op = 1 << 30;
+    for (int l = lo_layer; l < hi_layer; ++l) if (op_of_layer[l] < first_op) first_op = op_of_layer[l];
+    h->buckets.push_back(dr_handle::Bucket{h->layers[lo_layer].w_off, hi_off, first_op});
+    hi_layer = lo_layer;
+  }
+}
+
+// all-reduce(sum) of grads[lo,hi) on the communication stream, after everything enqueued so far on `st` and on the wgrad stream
+int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st) {
+  NcclApi& a = nccl_api();
+  CUDA_TRY(h, cudaEventRecord(h->ev_bucket_main, st));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_main, 0));
+  if (h->side_stream && h->wgrad_stream) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_bucket_side, h->wgrad_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_side, 0));
+  }
+  const int rc = a.all_reduce(h->grads + lo, h->grads + lo, (size_t)(hi - lo), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, h->comm_stream);
+  if (rc != 0) return nccl_fail(h, "ncclAllReduce", rc);
+  ++h->allreduce_calls;
   return DR_OK;
 }
 
@@ -774,6 +892,11 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
 
 int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
+  if (h->nccl_comm) { nccl_api().comm_destroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_bucket_main) cudaEventDestroy(h->ev_bucket_main);
+  if (h->ev_bucket_side) cudaEventDestroy(h->ev_bucket_side);
+  if (h->ev_comm_done) cudaEventDestroy(h->ev_comm_done);
   if (h->infer_graph.exec) cudaGraphExecDestroy(h->infer_graph.exec);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
@@ -802,6 +925,19 @@ int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, vo
     }
   }
   return DR_ERR_ARG;
+}
+
+int dr_trace(dr_handle* h, int on) {
+  if (!h) return DR_ERR_ARG;
+  h->trace_on = on != 0;
+  if (on) h->trace.clear();
+  return DR_OK;
+}
+int dr_trace_count(const dr_handle* h) { return h ? (int)h->trace.size() : 0; }
+int dr_trace_get(const dr_handle* h, int idx, dr_trace_rec* out) {
+  if (!h || !out || idx < 0 || idx >= (int)h->trace.size()) return DR_ERR_ARG;
+  *out = h->trace[idx];
+  return DR_OK;
 }
 
 int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
@@ -953,6 +1089,43 @@ int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses
   return backward_impl(h, B, poses_mm, cfgs, coms, loss_out, st);
 }
 
+int dr_comm_unique_id(void* out128) {
+  if (!out128) return DR_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return DR_ERR_UNSUPPORTED;
+  return a.get_unique_id(out128) == 0 ? DR_OK : DR_ERR_CUDA;
+}
+
+int dr_comm_init(dr_handle* h, int rank, int world, const void* nccl_unique_id128) {
+  if (!h || world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_unique_id128)) return DR_ERR_ARG;
+  if (h->nccl_comm) return fail(h, DR_ERR_STATE, "dr_comm_init called twice");
+  h->comm_rank = rank; h->comm_world = world;
+  if (world == 1) return DR_OK;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return fail(h, DR_ERR_UNSUPPORTED, "libnccl.so.2 not found (dlopen)");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DrNcclId id; memcpy(&id, nccl_unique_id128, sizeof(id));
+  void* comm = nullptr;
+  const int rc = reinterpret_cast<NcclApi::CommInitRank_t>(a.comm_init_rank)(&comm, world, id, rank);
+  if (rc != 0) return nccl_fail(h, "ncclCommInitRank", rc);
+  h->nccl_comm = comm;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bucket_main, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bucket_side, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming));
+  int nb = 4; { const char* e = getenv("DENSEREG_COMM_BUCKETS"); if (e && atoi(e) > 0) nb = atoi(e); }
+  plan_buckets(h, nb);
+  return DR_OK;
+}
+
+int dr_comm_overlap_next_backward(dr_handle* h) {
+  if (!h) return DR_ERR_ARG;
+  h->overlap_armed = h->nccl_comm != nullptr && h->comm_world > 1;
+  return DR_OK;
+}
+
+int64_t dr_comm_allreduce_count(const dr_handle* h) { return h ? h->allreduce_calls : 0; }
+
 int dr_zero_grads(dr_handle* h, void* stream) {
   if (!h) return DR_ERR_ARG;
   if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
@@ -963,10 +1136,27 @@ int dr_zero_grads(dr_handle* h, void* stream) {
 int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_t step, void* stream) {
   if (!h || accum_steps < 1 || world < 1 || step < 1) return DR_ERR_ARG;
   if (!h->grads || !h->adam_m || !h->adam_v || !h->params) return fail(h, DR_ERR_STATE, "grads / adam buffers not bound");
-  const double b1 = 0.5, b2 = 0.999;                       // hourglass_um_crop_tiny.py:77,439
-  const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step)));
-  h->launches += launch_adam(h->n_params, h->params, h->grads, h->adam_m, h->adam_v, 1.0f / (float)(accum_steps * world), 0.2f,
-                             lr_t, (float)b1, (float)b2, 1e-8f, (cudaStream_t)stream);
+  cudaStream_t ost = (cudaStream_t)stream;
+  if (h->nccl_comm && h->comm_world > 1) {
+    if (world != h->comm_world) return fail(h, DR_ERR_ARG, "dr_optimizer_step: world differs from the communicator's size");
+    if (!h->reduced_in_backward) {                          // not overlapped with the last backward: one all-reduce of the whole buffer now
+      int rc = reduce_range(h, 0, (int64_t)h->n_params, ost);
+      if (rc) return rc;
+      CUDA_TRY(h, cudaEventRecord(h->ev_comm_done, h->comm_stream));
+    }
+    CUDA_TRY(h, cudaStreamWaitEvent(ost, h->ev_comm_done, 0));
+    h->reduced_in_backward = false;
+  }
+  // hourglass_um_crop_tiny.py:77,439; TF ApplyAdam arithmetic in fp32: beta powers by repeated fp32 multiplication (TF keeps them as
+  // fp32 variables), alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+  const float b1 = 0.5f, b2 = 0.999f;
+  if (step == h->pow_step + 1) { h->b1p *= b1; h->b2p *= b2; }                 // the usual case: one multiplication per step, like TF's update of its power variables
+  else { h->b1p = 1.0f; h->b2p = 1.0f; for (int64_t t = 0; t < step; ++t) { h->b1p *= b1; h->b2p *= b2; if (h->b1p == 0.0f && h->b2p == 0.0f) break; } }
+  h->pow_step = step;
+  const float b1p = h->b1p, b2p = h->b2p;
+  const float alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+  h->launches += launch_adam(h->n_params, h->params, h->grads, h->adam_m, h->adam_v, (float)(accum_steps * world), 0.2f,
+                             alpha, 1.0f - b1, 1.0f - b2, 1e-8f, ost);
   h->weights_dirty = true;
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;

@@ -86,7 +86,7 @@ __global__ void maxpool_kernel(int B, int H, int W, int C, int k, const float* _
 // float4-over-channels variant of maxpool_bwd_kernel (C, strides % 4 == 0, 16 B aligned views): same gather formulation and the same
 // "first maximum in (dy, dx) scan order wins" tie rule per channel, one thread per (input pixel, channel quad) -- a quarter of the load
 // instructions (the scalar kernel issues up to 36 loads of x per element on the 3x3/s2 pools: 192 us for the 32x32 -> 16x16 pool at B=40).
-// Opt-in (DENSEREG_POOL_BWD_V4=1) until verified on the GPU.
+// Default since round 2 (verified against the fp32 engine and measured: profiles/r2_sweep.md); DENSEREG_POOL_BWD_V4=0 selects the scalar kernel.
 __global__ void maxpool_bwd_v4_kernel(int B, int H, int W, int C4, int k, const float4* __restrict__ x, int x_cs4,
                                       const float4* __restrict__ dy, int dy_cs4, float4* __restrict__ dx, int dx_cs4, int accumulate) {
   const int Ho = H / 2, Wo = W / 2;
@@ -422,80 +422,6 @@ __global__ void brn_bwd_apply_v4_kernel(unsigned npix, unsigned C4, const float4
   }
 }
 
-// BRN backward in ONE cooperative launch: phase 1 = per-channel reductions (sum g, sum g*xhat; same mapping as
-// brn_bwd_reduce_kernel), grid-wide barrier (all blocks are co-resident: cudaLaunchCooperativeKernel), phase 2 = d(raw) (float4,
-// same arithmetic as brn_bwd_apply_v4_kernel) + d(beta), d(gamma).  Halves the launches and latency floors of the BRN backward.
-__global__ void brn_bwd_fused_kernel(unsigned npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ raw, int raw_cs,
-                                     const float* __restrict__ aff, const float* __restrict__ bstat, const float* __restrict__ bg, int relu,
-                                     double* __restrict__ sums, unsigned int* __restrict__ counter, float* __restrict__ draw, int draw_cs,
-                                     float* __restrict__ gparam) {
-  __shared__ double s1[8][33], s2[8][33];
-  {
-    const int c = blockIdx.x * 32 + threadIdx.x;
-    double a = 0.0, b = 0.0;
-    if (c < C) {
-      const float sa = aff[c], sb = aff[C + c], mean = bstat[c], inv_std = bstat[C + c];
-      for (size_t p = blockIdx.y * 8 + threadIdx.y; p < npix; p += (size_t)gridDim.y * 8) {
-        const float x = raw[p * raw_cs + c];
-        float g = dy[p * dy_cs + c];
-        if (relu && !(x * sa + sb > 0.f)) g = 0.f;
-        const float xh = (x - mean) * inv_std;
-        a += (double)g; b += (double)g * (double)xh;
-      }
-    }
-    s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-      for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-      atomicAdd(sums + c, a); atomicAdd(sums + C + c, b);
-    }
-  }
-  // ---- grid barrier -------------------------------------------------------------------------------------------------
-  const unsigned nblocks = gridDim.x * gridDim.y;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    atomicAdd(counter, 1u);
-    while (*((volatile unsigned int*)counter) < nblocks) __nanosleep(32);
-  }
-  __syncthreads();
-  __threadfence();
-  // ---- phase 2 ------------------------------------------------------------------------------------------------------
-  const unsigned C4 = (unsigned)C / 4, n4 = npix * C4;
-  const unsigned lin = (blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 + threadIdx.x;
-  const double inv_n = 1.0 / (double)npix;
-  const float4* dy4 = reinterpret_cast<const float4*>(dy); const float4* raw4 = reinterpret_cast<const float4*>(raw);
-  float4* draw4 = reinterpret_cast<float4*>(draw);
-  const unsigned dy_cs4 = dy_cs / 4, raw_cs4 = raw_cs / 4, draw_cs4 = draw_cs / 4;
-  for (unsigned i = lin; i < n4; i += nblocks * 256) {
-    const unsigned pix = i / C4, cq = i - pix * C4;
-    const float4 x4 = raw4[(size_t)pix * raw_cs4 + cq], g4 = dy4[(size_t)pix * dy_cs4 + cq];
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-    const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
-    float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = (int)cq * 4 + e;
-      const float sa = __ldg(aff + c), sb = __ldg(aff + C + c), mean = __ldg(bstat + c), inv_std = __ldg(bstat + C + c), r = __ldg(bstat + 2 * C + c);
-      const float gamma = __ldg(bg + C + c);
-      float g = gs[e];
-      if (relu && !(xs[e] * sa + sb > 0.f)) g = 0.f;
-      const float xh = (xs[e] - mean) * inv_std;
-      const float mg = (float)(__ldcg(sums + c) * inv_n), mgx = (float)(__ldcg(sums + C + c) * inv_n);
-      o[e] = gamma * r * inv_std * (g - mg - xh * mgx);
-    }
-    draw4[(size_t)pix * draw_cs4 + cq] = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    for (int c = threadIdx.y * 32 + threadIdx.x; c < C; c += 256) {
-      const float r = bstat[2 * C + c], d = bstat[3 * C + c];
-      const double sg = __ldcg(sums + c), sgx = __ldcg(sums + C + c);
-      gparam[c] += (float)sg;
-      gparam[C + c] += (float)((double)r * sgx + (double)d * sg);
-    }
-  }
-}
-
 // float4 copy / accumulate of a view (optional depth mask)
 __global__ void copy_view_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ src, unsigned src_cs4, float4* __restrict__ dst,
                                     unsigned dst_cs4, int accumulate, const float* __restrict__ tiny_mask) {
@@ -604,15 +530,17 @@ __global__ void finish_loss_kernel(const double* __restrict__ acc, float* __rest
   out5[0] = (float)t; out5[1] = (float)acc[0]; out5[2] = (float)acc[1]; out5[3] = (float)acc[2]; out5[4] = (float)acc[3];
 }
 
+// TF ApplyAdam form (oracle/um_v1_torch.py adam_step): m += (g - m)(1 - b1); v += (g*g - v)(1 - b2); p -= (m * alpha) / (sqrt(v) + eps),
+// every operation a separate fp32 rounding (no FMA contraction), omb1 / omb2 = the fp32 differences 1.0f - beta.
 __global__ void adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            float inv_scale, float clip, float lr_t, float b1, float b2, float eps) {
+                            float inv_scale, float clip, float alpha, float omb1, float omb2, float eps) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * inv_scale;
+    float gi = __fdiv_rn(g[i], inv_scale);                  // inv_scale carries accum_steps * world: the mean is a division, as in the reference
     gi = fminf(fmaxf(gi, -clip), clip);
-    float mi = b1 * m[i] + (1.0f - b1) * gi;
-    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), omb1));
+    const float vi = __fadd_rn(v[i], __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), v[i]), omb2));
     m[i] = mi; v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = __fsub_rn(p[i], __fdiv_rn(__fmul_rn(mi, alpha), __fadd_rn(__fsqrt_rn(vi), eps)));
   }
 }
 
@@ -664,7 +592,7 @@ int launch_maxpool_bwd(int B, int H, int W, int C, int k, const float* x, int x_
                        float* dx, int dx_cs, int accumulate, cudaStream_t st) {
   size_t n = (size_t)B * H * W * C;
   static int v4 = -1;
-  if (v4 < 0) { const char* e = getenv("DENSEREG_POOL_BWD_V4"); v4 = (e && e[0] == '1') ? 1 : 0; }
+  if (v4 < 0) { const char* e = getenv("DENSEREG_POOL_BWD_V4"); v4 = (e && e[0] == '0') ? 0 : 1; }   // default on: -0.36 ms per micro-batch (profiles/r2_sweep.md)
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (v4 && C % 4 == 0 && x_cs % 4 == 0 && dy_cs % 4 == 0 && dx_cs % 4 == 0 && al(x) && al(dy) && al(dx)) {
     maxpool_bwd_v4_kernel<<<blocks_for(n / 4), EW_T, 0, st>>>(B, H, W, C / 4, k, (const float4*)x, x_cs / 4, (const float4*)dy, dy_cs / 4,
@@ -726,47 +654,11 @@ int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const flo
   }
   return 1;
 }
-// returns 0 (nothing launched) when the float4 / co-residency preconditions do not hold -> caller uses reduce + apply
-int launch_brn_bwd_fused(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs, const float* aff, const float* bstat,
-                         const float* beta_gamma, int relu, double* sums, unsigned int* counter, float* draw, int draw_cs, float* gparam,
-                         cudaStream_t st) {
-  static int max_blocks = -1;
-  if (max_blocks < 0) {
-    // measured on B200: the cooperative launch + grid barrier is SLOWER than two plain launches (1038 vs 1247 crops/s), so this
-    // path is opt-in (DENSEREG_BRN_BWD_FUSED=1) and the default is reduce + apply
-    const char* env = getenv("DENSEREG_BRN_BWD_FUSED");
-    if (!env || env[0] != '1') { max_blocks = 0; return 0; }
-    int dev = 0, sms = 0, per_sm = 0, coop = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brn_bwd_fused_kernel, 256, 0);
-    max_blocks = coop ? sms * per_sm : 0;
-  }
-  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (max_blocks <= 0 || C % 4 != 0 || raw_cs % 4 != 0 || dy_cs % 4 != 0 || draw_cs % 4 != 0 || !al(raw) || !al(dy) || !al(draw) ||
-      npix * (size_t)(C / 4) >= 0xFFFFFFFFull)
-    return 0;
-  dim3 grid = stats_grid(npix, C);
-  int cap = max_blocks / 2;                               // leave room: other kernels of the stream may still be draining
-  if (cap < 1) return 0;
-  if ((int)(grid.x * grid.y) > cap) {
-    unsigned gy = cap / grid.x;
-    if (gy < 1) return 0;
-    grid.y = gy;
-  }
-  unsigned np = (unsigned)npix;
-  void* args[] = {&np, &C, &dy, &dy_cs, &raw, &raw_cs, &aff, &bstat, &beta_gamma, &relu, &sums, &counter, &draw, &draw_cs, &gparam};
-  if (cudaLaunchCooperativeKernel((void*)brn_bwd_fused_kernel, grid, dim3(32, 8), args, 0, st) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return 1;
-}
 // block / grid of the channel-stationary float4 kernels: blockDim = C4 * floor(256 / C4); every thread gets >= 8 pixels when there are enough.
 // `cap` bounds the grid.  The reduce kernel ends with 2*C double atomics per BLOCK onto 2*C addresses (64 lines at C = 512), so its time grows
 // with the block count once the atomics serialise: 1184 blocks x 16 atomics per line = 19 k atomics per line ~ 20 us per launch, twice the
-// streaming time (profiles/r1_final.md section 4) -> 2 blocks per SM for the reduce (still > 9 MB of loads in flight), 8 per SM for the apply.
+// streaming time (profiles/r1_final.md section 4) -> ONE block per SM for the reduce (round-2 sweep: 148 -> 20.90, 296 -> 20.95, 592 -> 21.40,
+// 1184 -> 21.76 ms per micro-batch), 8 per SM for the apply.
 // DENSEREG_BRN_BLOCKS overrides both.
 static bool brn_v4_shape(size_t npix, int C, unsigned* block, unsigned* grid, size_t cap) {
   const unsigned C4 = (unsigned)C / 4;
@@ -786,7 +678,7 @@ int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const 
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   unsigned block, grid;
-  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid, 148 * 2)) {
+  if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid, 148)) {
     brn_bwd_reduce_v4_kernel<<<grid, block, (size_t)block * 4 * 2 * sizeof(double), st>>>((unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4,
                                                                                         (const float4*)raw, raw_cs / 4, aff, bstat, relu, sums);
     return 1;
@@ -826,9 +718,9 @@ int launch_finish_loss(const double* acc, float* out5, cudaStream_t st) {
   finish_loss_kernel<<<1, 1, 0, st>>>(acc, out5);
   return 1;
 }
-int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float inv_scale, float clip,
-                float lr_t, float b1, float b2, float eps, cudaStream_t st) {
-  adam_kernel<<<blocks_for(n, EW_T * 4, 148 * 8), EW_T, 0, st>>>(n, p, g, m, v, inv_scale, clip, lr_t, b1, b2, eps);
+int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float divisor, float clip,
+                float alpha, float omb1, float omb2, float eps, cudaStream_t st) {
+  adam_kernel<<<blocks_for(n, EW_T * 4, 148 * 8), EW_T, 0, st>>>(n, p, g, m, v, divisor, clip, alpha, omb1, omb2, eps);
   return 1;
 }
 int launch_init_trunc_normal(size_t n, float* p, float stddev, uint64_t seed, cudaStream_t st) {

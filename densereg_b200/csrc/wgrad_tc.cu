@@ -197,207 +197,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 }
 
 
-// ---- persistent variant (opt-in, DENSEREG_WGRAD_PERSIST=1) ---------------------------------------------------------------------------
-// Same tile arithmetic as wgrad_tc_kernel, scheduled like conv_tc_kernel: one CTA per SM walks work items
-// (split, tap, m tile, n tile) -- n fastest, split slowest, so that concurrently running CTAs share the same pixel range of X and dY in L2 --
-// with the shared-memory ring running across items and the accumulator double-buffered in TMEM (2 x BN columns): the reductions of item i
-// into the flat gradient overlap the main loop of item i+1, and TMEM allocation / barrier setup / tensor-map fetch happen once per CTA
-// instead of once per item (the one-shot kernel spends ~40 % of its time there: ~25 us of fixed cost per CTA against a 36 us main loop on the
-// 128->128 3x3 layers, profiles/r1_final.md section 6).
-template <bool SPLIT3>
-__global__ void __launch_bounds__(SPLIT3 ? 192 + WG_SPLIT_THREADS : 192, 1)
-wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.nchunks_b * WG_CHUNK_BYTES;
-  const int stage_bytes = (SPLIT3 ? 2 : 1) * (WG_A_BYTES + b_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* split_bar = empty_bar + p.stages;
-  uint64_t* acc_full = split_bar + p.stages;        // [2]
-  uint64_t* acc_empty = acc_full + 2;               // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = p.ksz * p.ksz * p.cin_tiles * p.n_tiles;
-  const int total_items = tiles * p.splits;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], WG_SPLIT_THREADS / 32); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // item -> (split, tap, first M row, first N column, k-block range)
-  struct Item { int tap, c0, n0, kb_begin, num_kb; };
-  auto decode = [&](int item) {
-    Item it;
-    const int split = item / tiles, tile = item - split * tiles;
-    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-    it.tap = mt / p.cin_tiles;
-    it.c0 = (mt - it.tap * p.cin_tiles) * 128;
-    it.n0 = nt * p.BN;
-    it.kb_begin = split * p.kb_per_split;
-    int kb_end = it.kb_begin + p.kb_per_split;
-    if (kb_end > p.total_kb) kb_end = p.total_kb;
-    it.num_kb = kb_end - it.kb_begin;                // >= 1 by construction of splits
-    return it;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)(WG_A_BYTES + b_bytes);
-      uint32_t ring = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Item w = decode(item);
-        const int dy = w.tap / p.ksz - p.pad, dx = w.tap % p.ksz - p.pad;
-        for (int i = 0; i < w.num_kb; ++i, ++ring) {
-          const int s = ring % p.stages;
-          const uint32_t ph = (ring / p.stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          const int pix = (w.kb_begin + i) * WG_KB;
-          const int img = pix / (p.H * p.W);
-          const int rem = pix - img * p.H * p.W;
-          const int y = rem / p.W, x = rem - y * p.W;
-          uint8_t* st = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], tx);
-          if (!p.swap) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_4d(&map_x, &full_bar[s], st + j * WG_CHUNK_BYTES, w.c0 + 32 * j, x + dx, y + dy, img);
-            for (int j = 0; j < p.nchunks_b; ++j)
-              tma_load_4d(&map_dy, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, w.n0 + 32 * j, x, y, img);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_4d(&map_dy, &full_bar[s], st + j * WG_CHUNK_BYTES, w.c0 + 32 * j, x, y, img);
-            for (int j = 0; j < p.nchunks_b; ++j)
-              tma_load_4d(&map_x, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, w.n0 + 32 * j, x + dx, y + dy, img);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t ring = 0, tcount = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tcount) {
-        const Item w = decode(item);
-        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
-        for (int i = 0; i < w.num_kb; ++i, ++ring) {
-          const int s = ring % p.stages;
-          const uint32_t ph = (ring / p.stages) & 1;
-          if (SPLIT3) mbar_wait(&split_bar[s], ph); else mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + WG_A_BYTES;
-          const uint32_t lo_off = (uint32_t)(WG_A_BYTES + b_bytes);
-#pragma unroll
-          for (int k = 0; k < WG_KB / 8; ++k) {
-            const uint64_t ad = make_desc_mn(a_addr + k * 1024, WG_CHUNK_BYTES, 512);
-            const uint64_t bd = make_desc_mn(b_addr + k * 1024, WG_CHUNK_BYTES, 512);
-            if (SPLIT3) {
-              const uint64_t ald = make_desc_mn(a_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
-              const uint64_t bld = make_desc_mn(b_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
-              tc_mma_tf32(tmem_d, ad, bld, idesc, (i | k) != 0);
-              tc_mma_tf32(tmem_d, ald, bd, idesc, 1);
-              tc_mma_tf32(tmem_d, ad, bd, idesc, 1);
-            } else {
-              tc_mma_tf32(tmem_d, ad, bd, idesc, (i | k) != 0);
-            }
-          }
-          tc_commit(&empty_bar[s]);
-        }
-        tc_commit(&acc_full[as]);
-      }
-    }
-  } else if (warp < 6) {
-    const int q = warp & 3;
-    uint32_t tcount = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tcount) {
-      const Item w = decode(item);
-      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-      mbar_wait_sleep(&acc_full[as], aph);
-      tc_fence_after();
-      const int c = w.c0 + q * 32 + lane;                   // TMEM lane == M row: cin (cout when swapped)
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.BN;
-      if (!p.swap) {
-        const bool cvalid = c < p.Cin;
-        float* row = p.dw + ((size_t)w.tap * p.Cin + c) * p.Cout;
-        for (int cb = 0; cb < p.BN; cb += 32) {
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)cb, v);
-          if (!cvalid) continue;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = w.n0 + cb + e;
-            if (n < p.Cout) atomicAdd(row + n, __uint_as_float(v[e]));
-          }
-        }
-      } else {
-        const bool cvalid = c < p.Cout;
-        float* col = p.dw + (size_t)w.tap * p.Cin * p.Cout + c;
-        for (int cb = 0; cb < p.BN; cb += 32) {
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)cb, v);
-          if (!cvalid) continue;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = w.n0 + cb + e;
-            if (n < p.Cin) atomicAdd(col + (size_t)n * p.Cout, __uint_as_float(v[e]));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);           // this warp's TMEM reads of the stage are complete
-    }
-  } else if (SPLIT3) {
-    const int t = threadIdx.x - 192;
-    const int n16 = (WG_A_BYTES + b_bytes) / 16;
-    uint32_t ring = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Item w = decode(item);
-      for (int i = 0; i < w.num_kb; ++i, ++ring) {
-        const int s = ring % p.stages;
-        const uint32_t ph = (ring / p.stages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + WG_A_BYTES + b_bytes);
-        for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
-          float4 a = hi[idx], h, l;
-          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
-          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
-          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
-          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
-          hi[idx] = h; lo[idx] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[s]);
-      }
-    }
-  }
-
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
-  }
-}
-
-
 // ---- persistent 3xTF32 variant with the split A operand in TENSOR MEMORY (opt-in, DENSEREG_WGRAD_A_TMEM=1) ----------------------------------
-// As wgrad_tc_persist_kernel<true>, but the A tile (X^T, or dY^T when swapped) is split into tensor memory instead of shared memory: splitter
+// Persistent (one CTA per SM walks (split, tap, m tile, n tile) work items, shared-memory ring across items, two accumulator stages in tensor
+// memory so that the reductions of item i overlap the main loop of item i+1); the A tile (X^T, or dY^T when swapped) is split into tensor memory instead of shared memory: splitter
 // warp w owns tensor-memory lane quarter w % 4 = 32-channel chunk w % 4 of the tile (smem [chunk][pixel][32 channels]); for every pixel the
 // warp reads that pixel's 128 B row (conflict-free), so lane i collects channel i over the pixels = one K-major A row; hi / lo go out with
 // tcgen05.st and the MMAs use the [d], [a-tmem], b-desc form (A from tensor memory is K-major; B = the other operand stays MN-major in
@@ -648,7 +450,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   // MMA work pad128(M) x pad32(N): Cin = 64 / 80 layers with a wider Cout stop wasting 37-50 % of the MMA rows, and the epilogue's reductions
   // become one 128 B line per instruction (lane = cout) instead of 32 lines (lane = cin row).  Opt-in until measured on the GPU.
   static int swap_mode = -1;
-  if (swap_mode < 0) { const char* e = getenv("DENSEREG_WGRAD_SWAP"); swap_mode = e ? atoi(e) : 0; }
+  if (swap_mode < 0) { const char* e = getenv("DENSEREG_WGRAD_SWAP"); swap_mode = e ? atoi(e) : 1; }   // default 1 since round 2: -0.86 ms per micro-batch
   auto pad = [](int v, int m) { return (v + m - 1) / m * m; };
   const long long work_std = (long long)pad(p.Cin, 128) * pad(p.Cout, 32), work_swp = (long long)pad(p.Cout, 128) * pad(p.Cin, 32);
   t.swap = (swap_mode == 1 && work_swp <= work_std) || swap_mode == 2;
@@ -663,16 +465,14 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   const int cout_tiles = (Ndim + BN - 1) / BN;
   const int tiles = t.cin_tiles * p.k * p.k * cout_tiles;
   static int waves = 0;
-  if (!waves) { const char* e = getenv("DENSEREG_WGRAD_WAVES"); waves = e && atoi(e) > 0 ? atoi(e) : 2; }   // tuning knob (persistent kernel: try 3-4)
+  if (!waves) { const char* e = getenv("DENSEREG_WGRAD_WAVES"); waves = e && atoi(e) > 0 ? atoi(e) : 1; }   // round-2 sweep: 1 wave 19.94, 2 waves 20.95, 3 waves 21.58 ms per micro-batch
   int splits = (waves * 148) / tiles;                       // floor: keep the CTA count just under `waves` full waves of 148 SMs
   if (splits > t.total_kb / 8) splits = t.total_kb / 8;
   if (splits < 1) splits = 1;
   t.kb_per_split = (t.total_kb + splits - 1) / splits;
   splits = (t.total_kb + t.kb_per_split - 1) / t.kb_per_split;
-  static int persist = -1;
-  if (persist < 0) { const char* e = getenv("DENSEREG_WGRAD_PERSIST"); persist = (e && e[0] == '1') ? 1 : 0; }
   t.n_tiles = cout_tiles; t.splits = splits;
-  int cols = 32; while (cols < (persist ? 2 * BN : BN)) cols <<= 1;      // persistent kernel: two accumulator stages
+  int cols = 32; while (cols < BN) cols <<= 1;
   t.tmem_cols = cols;
   const int stage_bytes = (split3 ? 2 : 1) * (WG_A_BYTES + t.nchunks_b * WG_CHUNK_BYTES);
   int stages = (208 * 1024) / stage_bytes;
@@ -717,22 +517,6 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
       wgrad_tc_atmem_kernel<<<dim3(total_items < num_sms_a ? total_items : num_sms_a), 192 + WG_SPLIT_THREADS, asmem, st>>>(mx, mdy, ta);
       return launch_ok(cudaPeekAtLastError(), "wgrad_tc_atmem_kernel") ? 1 : 0;
     }
-  }
-  if (persist) {
-    static bool pattr[2] = {false, false};
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
-    const int total_items = tiles * splits;
-    const size_t psmem = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 16 + 1024 + 64;
-    dim3 pgrid(total_items < num_sms ? total_items : num_sms);
-    if (split3) {
-      if (!pattr[1]) { cudaFuncSetAttribute(wgrad_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); pattr[1] = true; }
-      wgrad_tc_persist_kernel<true><<<pgrid, 192 + WG_SPLIT_THREADS, psmem, st>>>(mx, mdy, t);
-    } else {
-      if (!pattr[0]) { cudaFuncSetAttribute(wgrad_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); pattr[0] = true; }
-      wgrad_tc_persist_kernel<false><<<pgrid, 192, psmem, st>>>(mx, mdy, t);
-    }
-    return launch_ok(cudaPeekAtLastError(), "wgrad_tc_persist_kernel") ? 1 : 0;
   }
   dim3 grid(t.cin_tiles * p.k * p.k, cout_tiles, splits);
   if (split3) {

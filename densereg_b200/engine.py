@@ -169,6 +169,43 @@ class DenseRegEngine:
                                          _ptr(edge_ratio), _ptr(dms_out), _ptr(poses_out), self._stream()))
         return dms_out, poses_out
 
+    # ---- data-parallel communicator (replaces model/train_multi_gpu.py:16-39) ---------------------------------
+    def comm_init(self, rank, world, unique_id=None):
+        """Create the in-library NCCL communicator.  `unique_id`: 128 bytes from rank 0's comm_unique_id(); when None and
+        torch.distributed is initialised, rank 0's id is broadcast through it (plumbing only -- the gradient all-reduce itself runs
+        inside libdensereg_sm100.so)."""
+        self.rank, self.world = rank, world
+        if world == 1:
+            return
+        if unique_id is None:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise DenseRegError("comm_init needs a unique id or an initialised torch.distributed group to broadcast it")
+            dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+            buf = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).clone()
+            buf = buf.to(dev)
+            dist.broadcast(buf, src=0)
+            unique_id = bytes(buf.cpu().numpy().tobytes())
+        idbuf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.dr_comm_init(self._h, rank, world, C.cast(idbuf, C.c_void_p)))
+
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self.lib.dr_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise DenseRegError("dr_comm_unique_id failed with %d (libnccl.so.2 not found?)" % rc)
+        return bytes(buf.raw)
+
+    def comm_overlap_next_backward(self):
+        """The next loss_backward() is the last micro-batch of the optimiser step: all-reduce gradient buckets as they become final."""
+        self._check(self.lib.dr_comm_overlap_next_backward(self._h))
+
+    @property
+    def allreduce_count(self):
+        return int(self.lib.dr_comm_allreduce_count(self._h))
+
     def zero_grads(self):
         self._check(self.lib.dr_zero_grads(self._h, self._stream()))
 
@@ -192,7 +229,7 @@ class DenseRegEngine:
         return y
 
     def debug_conv_bwd(self, layer, x, dy, precision="fp32", want_dx=True):
-        L = self.layers()[layer]
+        L = self._layers_cached()[layer]
         dx = torch.empty_like(x) if want_dx else None
         dw = torch.empty(L["k"] * L["k"] * L["cin"] * L["cout"], dtype=torch.float32, device=self.device)
         self._check(self.lib.dr_debug_conv_bwd(self._h, layer, x.shape[0], _ptr(x), _ptr(dy), _ptr(dx), _ptr(dw),
@@ -200,9 +237,22 @@ class DenseRegEngine:
         return dx, dw
 
     def debug_get_output(self, layer, B, grad=False):
-        L = self.layers()[layer]
+        L = self._layers_cached()[layer]
         out = torch.empty(B, L["out_hw"], L["out_hw"], L["cout"], dtype=torch.float32, device=self.device)
         self._check(self.lib.dr_debug_get_output(self._h, layer, B, _ptr(out), int(grad), self._stream()))
+        return out
+
+    def trace(self, on=True):
+        """Per-launch timing of the conv-type kernels (serialises them; measurement passes only)."""
+        self._check(self.lib.dr_trace(self._h, int(on)))
+
+    def trace_records(self):
+        out = []
+        rec = _ffi.DrTraceRec()
+        for i in range(self.lib.dr_trace_count(self._h)):
+            self._check(self.lib.dr_trace_get(self._h, i, C.byref(rec)))
+            out.append(dict(kind=("conv", "dgrad", "wgrad")[rec.kind], B=rec.B, hw=rec.hw, cin=rec.cin, cout=rec.cout, k=rec.k,
+                            kernel=("ffma", "tcgen05", "tcgen05_pair")[rec.kernel], ms=rec.ms))
         return out
 
     @property

@@ -134,14 +134,28 @@ DR_API int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float
                      const float* cfgs, const float* coms, float* loss_out,
                      uint64_t dropout_seed, int update_state, void* stream);
 
+/* Data-parallel communicator: replaces model/train_multi_gpu.py:16-39 (_average_gradients: per-variable concat + mean through host
+ * memory) and :63-64,73-92 (towers) with one process per GPU and ONE NCCL all-reduce(sum) of the flat gradient per optimiser step.
+ *   dr_comm_unique_id   rank 0 fills 128 bytes (ncclUniqueId); the caller ships them to the other ranks (any transport).
+ *   dr_comm_init        every rank, after dr_create: creates the communicator on the handle's device.  world == 1 is a no-op.
+ *   dr_comm_overlap_next_backward   call before the LAST dr_loss_backward of an optimiser step: that backward pass all-reduces the
+ *                       gradient in buckets (last layers first) on a communication stream as soon as each bucket is final, so the
+ *                       transfer overlaps the rest of the backward pass; dr_optimizer_step then only waits for it.  Without this call
+ *                       dr_optimizer_step all-reduces the whole buffer itself before the update.
+ * NCCL is resolved with dlopen("libnccl.so.2") at dr_comm_init time (inside a PyTorch process: the copy PyTorch already loaded). */
+DR_API int dr_comm_unique_id(void* out128);
+DR_API int dr_comm_init(dr_handle* h, int rank, int world, const void* nccl_unique_id128);
+DR_API int dr_comm_overlap_next_backward(dr_handle* h);
+DR_API int64_t dr_comm_allreduce_count(const dr_handle* h);
+
 /* reset_op (train_single_gpu.py:83) */
 DR_API int dr_zero_grads(dr_handle* h, void* stream);
 
 /* ave_grad + clip + Adam apply (train_single_gpu.py:86-88, hourglass_um_crop_tiny.py:436-439):
  * g = clip(grads / (accum_steps*world), +-0.2); Adam(beta1 .5, beta2 .999, eps 1e-8) with TF's
- * lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  `grads` must already hold the sum over micro-batches and
- * ranks (the host does ONE all-reduce(sum) on it, replacing model/train_multi_gpu.py:16-39).
- * step is the 1-based optimiser step. */
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  With a communicator (dr_comm_init, world > 1) the sum over ranks happens here (or was
+ * overlapped with the last backward pass, dr_comm_overlap_next_backward); without one, `grads` must already hold the sum over
+ * micro-batches and ranks.  step is the 1-based optimiser step. */
 DR_API int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_t step, void* stream);
 
 /* Depth-frame front-end ("next" row 8f-1): data/preprocess.py:10-79 crop_from_xyz_pose + :131-142 center_of_mass.
@@ -175,6 +189,19 @@ DR_API int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, con
  * forward/backward into dst (B,Ho,Wo,cout) dense.  For the last conv of a residual block this is the block
  * output (post-activation conv + skip), as in network/um_v1.py:48. */
 DR_API int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, void* stream);
+
+/* Per-launch timing of the conv-type kernels (measurement only; no reference counterpart).  dr_trace(h, 1) clears the record list and
+ * makes every conv / dgrad / wgrad launch time itself with CUDA events on its own stream (this serialises the launches: use it on a
+ * separate pass, never inside a timed region); dr_trace(h, 0) stops.  bench.py derives the per-class roofline from these records. */
+typedef struct {
+  int32_t kind;          /* 0 forward conv, 1 dgrad, 2 wgrad            */
+  int32_t B, hw, cin, cout, k;
+  int32_t kernel;        /* 0 FFMA, 1 tcgen05 one-CTA, 2 tcgen05 CTA pair */
+  float ms;
+} dr_trace_rec;
+DR_API int dr_trace(dr_handle* h, int on);
+DR_API int dr_trace_count(const dr_handle* h);
+DR_API int dr_trace_get(const dr_handle* h, int idx, dr_trace_rec* out);
 
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 DR_API int64_t dr_launch_count(const dr_handle* h);

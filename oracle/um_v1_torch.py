@@ -391,11 +391,21 @@ def lr_at(step, decay_steps, init_lr=1e-3, factor=0.1):
 def adam_step(params, grad_sum, m, v, step, lr, accum_steps=5, world=1, beta1=0.5, beta2=0.999, eps=1e-8, clip=0.2):
     """train_single_gpu.py:84-88 + tf.train.AdamOptimizer.
     grad_sum = sum of micro-batch grads (over accum_steps and ranks). step = 1-based Adam step.
-    Updates params, m, v in place (fp32)."""
+    Updates params, m, v in place (fp32).
+
+    Arithmetic form: TF's ApplyAdam kernel (tensorflow/core/kernels/training_ops.cc, TF 1.3, un-vendored) evaluates the recurrences of
+    B.12 entirely in fp32 as
+        alpha = lr * sqrt(1 - beta2_power) / (1 - beta1_power)      beta*_power = fp32 variables multiplied by beta* once per step
+        m += (g - m) * (1 - beta1);   v += (g*g - v) * (1 - beta2);   var -= (m * alpha) / (sqrt(v) + eps)
+    -- in particular (1 - beta2) is the fp32 difference 1.0f - 0.999f = 0.000999987..., not 0.001 (1.3e-5 apart)."""
+    f32 = np.float32
     with torch.no_grad():
         g = torch.clamp(grad_sum / float(accum_steps * world), -clip, clip)
-        lr_t = np.float32(lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step))
-        m.mul_(beta1).add_(g, alpha=1.0 - beta1)
-        v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
-        params.sub_(lr_t * m / (torch.sqrt(v) + eps))
+        b1p, b2p = f32(1.0), f32(1.0)
+        for _ in range(int(step)):
+            b1p = f32(b1p * f32(beta1)); b2p = f32(b2p * f32(beta2))
+        alpha = f32(f32(lr) * np.sqrt(f32(1.0) - b2p, dtype=f32) / (f32(1.0) - b1p))
+        m.add_((g - m) * float(f32(1.0) - f32(beta1)))
+        v.add_((g * g - v) * float(f32(1.0) - f32(beta2)))
+        params.sub_((m * float(alpha)) / (torch.sqrt(v) + eps))
     return params

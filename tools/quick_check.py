@@ -74,6 +74,17 @@ try:
     t_cpu = time.perf_counter() - t0
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * a.micro)
+    # host cost of enqueueing ONE micro-batch into an empty queue (no back-pressure from the GPU)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); eng.loss_backward(*data, dropout_seed=99); t_one = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    # per-class conv-type time of one micro-batch, every launch timed alone (serialised)
+    eng.trace(True); eng.loss_backward(*data, dropout_seed=98, update_state=False); torch.cuda.synchronize()
+    cls = {}
+    for r in eng.trace_records():
+        c = cls.setdefault(r["kind"] + ":" + r["kernel"], [0, 0.0]); c[0] += 1; c[1] += r["ms"]
+    eng.trace(False)
+    out["trace_ms"] = {k: [v[0], round(v[1], 3)] for k, v in sorted(cls.items())}
+    out["cpu_enqueue_one_micro_ms"] = t_one * 1e3
     out.update(ms_per_micro=ms, crops_per_s=B / ms * 1e3, launches_per_micro=(eng.launch_count - l0) / (reps * a.micro),
                cpu_enqueue_ms_per_micro=t_cpu * 1e3 / (reps * a.micro), tc_launches=eng.tc_launch_count)
 except Exception as e:  # noqa: BLE001
