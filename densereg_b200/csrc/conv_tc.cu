@@ -243,10 +243,10 @@ bool conv_tc_eligible(const ConvProblem& p) {
 
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
-  // two-level accumulation (kernel comment): DENSEREG_TC_CHUNK = k-blocks per partial accumulator, 0 = off.  3xTF32 only; chunked layers
-  // run on this kernel (the CTA-pair kernel's tensor memory is full with two 256-column accumulator stages).
-  static int chunk_kb = -1;
-  if (chunk_kb < 0) { const char* e = getenv("DENSEREG_TC_CHUNK"); chunk_kb = e ? atoi(e) : 0; if (chunk_kb < 0) chunk_kb = 0; }
+  // two-level accumulation (kernel comment): ConvProblem::chunk_kb = k-blocks per partial accumulator, 0 = off (the engine sets it: on for
+  // inference, off for training -- engine.cu).  3xTF32 only; chunked layers run on this kernel (the CTA-pair kernel's tensor memory is full
+  // with two 256-column accumulator stages).
+  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : 0;
   const int num_kb_all = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
   const bool chunked = split3 && chunk_kb > 0 && num_kb_all > chunk_kb;
   if (split3 && !chunked) {

@@ -201,7 +201,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // 0 = off (default), 1 = use for 3xTF32 layers the pair kernel does not take, 2 = prefer over the pair kernel
 int conv_tc_atmem_mode() {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("DENSEREG_TC_A_TMEM"); mode = e ? atoi(e) : 0; }
+  if (mode < 0) { const char* e = getenv("DENSEREG_TC_A_TMEM"); mode = e ? atoi(e) : 1; }   // default 1 since round 2: -0.43 ms per micro-batch (profiles/r2_sweep.md)
   return mode;
 }
 

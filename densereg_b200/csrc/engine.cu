@@ -83,6 +83,11 @@ struct dr_handle {
   // aligned / split weight copies are rebuilt only when the parameters changed (dr_optimizer_step, dr_init_params, dr_bind,
   // dr_params_changed) or another arithmetic mode asks for them -- not once per micro-batch
   bool weights_dirty = true; int prepped_precision = -1; bool prep_once = true;
+  // two-level accumulation of the 3xTF32 convs (conv_tc.cu): k-blocks per partial accumulator.  Inference (the path whose joint positions
+  // are compared with the reference in mm) sums ONE k-block = 32 input channels (12 MMAs) inside the tensor core; training keeps one level
+  // (its gradients sit on the fp32 noise floor of the graph either way, and the CTA-pair kernel has no room for a running sum).
+  // DENSEREG_TC_CHUNK overrides both, DENSEREG_TC_CHUNK_EVAL / DENSEREG_TC_CHUNK_TRAIN one of them.
+  int chunk_eval = 1, chunk_train = 0;
   // backward: filter gradients run on a side stream (they only feed the optimiser) so that they fill the SMs the small
   // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
   static const int kScratchSlots = 3;
@@ -579,6 +584,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
         p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         set_fwd_weights(h, L, h->precision, p);
+        p.chunk_kb = training ? h->chunk_train : h->chunk_eval;
         const float* aff = h->aff + L.aff_off;
         const float* res = o.res.buf >= 0 ? X.ptr(o.res) : nullptr;
         const int res_cs = o.res.buf >= 0 ? X.cs(o.res) : 0;
@@ -708,6 +714,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin; p.k = L.k; p.stride = 1;
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
           set_dgrad_weights(h, L, h->precision, p);
+          p.chunk_kb = h->chunk_train;
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
           RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
@@ -883,6 +890,9 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   // CTA-pair (cta_group::2) 3xTF32 kernel for the big layers: on by default; dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0 turns it off
   { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] >= 0 && !(env && env[0] == '0'); }
   { const char* env = getenv("DENSEREG_PREP_ONCE"); h->prep_once = !(env && env[0] == '0'); }
+  { const char* e = getenv("DENSEREG_TC_CHUNK"); if (e) { h->chunk_eval = h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; } }
+  { const char* e = getenv("DENSEREG_TC_CHUNK_EVAL"); if (e) h->chunk_eval = atoi(e) > 0 ? atoi(e) : 0; }
+  { const char* e = getenv("DENSEREG_TC_CHUNK_TRAIN"); if (e) h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; }
   Builder b{h, 0, 0, 0};
   b.build();
   if (b.plan_overflow) { delete h; return DR_ERR_UNSUPPORTED; }   // a gradient view with > 4 unwritten channel gaps (never on um_v1)
@@ -1200,6 +1210,7 @@ int dr_data_aug(dr_handle* h, int B, int hw, int J, const float* dms, const floa
 int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int precision, void* stream) {
   const bool reuse = (precision & 0x100) != 0 && h && h->wk;
   const int force_pair = (precision & 0x200) != 0;          // debug: CTA-pair kernel for this call regardless of the handle's setting
+  const int precision_flags = precision;
   precision &= 0xff;
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;
   if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
@@ -1209,6 +1220,7 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
   if (precision != DR_PREC_FP32 && !reuse) { int rc = ensure_prepped(h, precision, (cudaStream_t)stream); if (rc) return rc; }
   set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout; p.pair = force_pair ? 2 : 0;
+  p.chunk_kb = (precision_flags & 0x400) ? h->chunk_eval : 0;          // debug flag 0x400: two-level accumulation as in inference
   { int64_t nl = 0; RUN_TRY(nl, run_conv(h, p, precision, (cudaStream_t)stream)); h->launches += nl; }
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
