@@ -31,6 +31,7 @@ struct ConvProblem {
   int wk_ld;               // row length (floats, multiple of 4) of the K-major copy: Cin rounded up to 4
   int pair;                // 3xTF32 tensor-core path: allow the CTA-pair (cta_group::2) kernel for big layers (conv_tc_pair.cu)
   int chunk_kb;            // 3xTF32 tensor-core path: two-level accumulation, k-blocks (of 32 channels) per partial accumulator; 0 = one level
+  int chunk_min_kb;        // ... only for reductions longer than this many k-blocks
   float* y; int y_cs;      // output view
   // epilogue: v = acc*scale[n] + shift[n]; relu; dropout; + res; + beta*y_old
   const float* scale;      // may be null (=1)

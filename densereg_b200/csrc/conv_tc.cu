@@ -248,7 +248,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   // with two 256-column accumulator stages).
   const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : 0;
   const int num_kb_all = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
-  const bool chunked = split3 && chunk_kb > 0 && num_kb_all > chunk_kb;
+  const bool chunked = split3 && chunk_kb > 0 && num_kb_all > chunk_kb && num_kb_all > p.chunk_min_kb;   // short reductions stay one-level
   if (split3 && !chunked) {
     const bool pair_w = conv_tc_pair_wanted(p);
     const int am = conv_tc_atmem_mode();                   // opt-in: split A operand in tensor memory (conv_tc_atmem.cu)

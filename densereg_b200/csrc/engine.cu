@@ -36,8 +36,17 @@ enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UPADD = 2, OP_MASKCOPY = 3 };
 
 struct GradWrite { int acc = 0; int nfill = 0; View fill[4]; };
 
+// Lanes: the op list is a DAG, not a chain -- the `upper1` branch of every hourglass level is independent of the whole lower path
+// (um_v1.py:54-65), the hm3 head of the um head (:137-144), the masked um branch of the unmasked one (:143-149), a projection skip of the
+// block's c1->c2 chain (:31-47).  Every op is assigned a lane (= CUDA stream) when the graph is built; a build-time hazard analysis over
+// the buffer views each op reads / writes (forward: activations; backward: gradients) yields, per op, the events of other lanes it has to
+// wait for and whether it must record one.  Small-grid kernels of different lanes then share the GPU.
+constexpr int kLanes = 3;
+struct OpPlan { int nwait = 0; int wait_op[kLanes]; int record = 0; };
+
 struct Op {
   OpKind kind;
+  int lane = 0;
   int layer = -1;
   View in, out, res;
   int raw = -1;
@@ -87,12 +96,19 @@ struct dr_handle {
   // are compared with the reference in mm) sums ONE k-block = 32 input channels (12 MMAs) inside the tensor core; training keeps one level
   // (its gradients sit on the fp32 noise floor of the graph either way, and the CTA-pair kernel has no room for a running sum).
   // DENSEREG_TC_CHUNK overrides both, DENSEREG_TC_CHUNK_EVAL / DENSEREG_TC_CHUNK_TRAIN one of them.
-  int chunk_eval = 1, chunk_train = 0;
+  int chunk_eval = 1, chunk_train = 0, chunk_min_kb = 0;
   // backward: filter gradients run on a side stream (they only feed the optimiser) so that they fill the SMs the small
   // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
-  static const int kScratchSlots = 3;
+  static const int kSlotsPerLane = 3;
+  static const int kScratchSlots = kSlotsPerLane * kLanes;
   cudaStream_t wgrad_stream = nullptr;
-  cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr}, ev_wdone[3] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
+  cudaEvent_t ev_ready[kSlotsPerLane * kLanes] = {}, ev_wdone[kSlotsPerLane * kLanes] = {}, ev_join = nullptr;
+  // lanes (see OpPlan): lane 0 is the caller's stream
+  bool lanes_on = true;
+  cudaStream_t lane_stream[kLanes] = {};
+  std::vector<OpPlan> plan_fwd, plan_bwd;
+  std::vector<cudaEvent_t> ev_fwd, ev_bwd;
+  cudaEvent_t ev_pass_start = nullptr, ev_lane_done[kLanes] = {};
   bool side_stream = true;
   bool tc_pair = true;       // CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers (dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0: off)
   // inference CUDA graph (dr_config.reserved[0] != 0): the ~170 launches of dr_infer are captured once per (batch, pointers) key
@@ -151,6 +167,7 @@ struct Builder {
   dr_handle* h;
   int F, J, S;
   bool plan_overflow = false;
+  int cur_lane = 0;          // lane of the ops being appended
   int new_buf(int hw, int C, int raw = 0) {
     Buf b; b.H = hw; b.W = hw; b.C = C; b.Cs = C == 1 ? 1 : (C + 3) / 4 * 4; b.raw = raw;   // 1-channel maps stay dense
     size_t& total = raw ? h->raw_per_crop : h->act_per_crop;
@@ -177,7 +194,7 @@ struct Builder {
     return (int)h->layers.size() - 1;
   }
   void conv_op(int layer, View in, View out, View res = View(), int accumulate = 0, int dropout_tag = -1) {
-    Op o; o.kind = OP_CONV; o.layer = layer; o.in = in; o.out = out; o.res = res;
+    Op o; o.kind = OP_CONV; o.layer = layer; o.in = in; o.out = out; o.res = res; o.lane = cur_lane;
     o.accumulate = accumulate; o.dropout_tag = dropout_tag;
     const Layer& L = h->layers[layer];
     if (L.brn) o.raw = new_buf(L.out_hw, L.cout, 1);
@@ -185,7 +202,8 @@ struct Builder {
     if (sc > h->scratch_per_crop) h->scratch_per_crop = sc;
     h->ops.push_back(o);
   }
-  void residual(const std::string& name, View in, int cin, int cout, View dest, int hw) {
+  // skip_lane >= 0: the projection skip (if any) runs on that lane, next to the c1 -> c2 chain
+  void residual(const std::string& name, View in, int cin, int cout, View dest, int hw, int skip_lane = -1) {
     int hc = cin / 2;
     int L1 = add_layer(name + "/c1", 1, 1, cin, hc, 1, 1, 0.0005f, hw);
     int L2 = add_layer(name + "/c2", 3, 1, hc, hc, 1, 1, 0.0005f, hw);
@@ -195,23 +213,31 @@ struct Builder {
     conv_op(L1, in, V(t1));
     conv_op(L2, V(t1), V(t2));
     View sk = in;
-    if (Ls >= 0) { int sb = new_buf(hw, cout); conv_op(Ls, in, V(sb)); sk = V(sb); }
+    if (Ls >= 0) {
+      int sb = new_buf(hw, cout);
+      const int keep = cur_lane;
+      if (skip_lane >= 0) cur_lane = skip_lane;
+      conv_op(Ls, in, V(sb)); sk = V(sb);
+      cur_lane = keep;
+    }
     conv_op(L3, V(t2), dest, sk);
   }
   void hourglass(const std::string& name, int n, View x, View dest, int hw) {
     char tag[16]; snprintf(tag, sizeof(tag), "/n%d", n);
     std::string p = name + tag;
     int up1 = new_buf(hw, F);
-    residual(p + "/upper1", x, F, F, V(up1), hw);
+    { const int keep = cur_lane; cur_lane = 1 + (n & 1);                      // the upper branch of level n overlaps the whole lower path
+      residual(p + "/upper1", x, F, F, V(up1), hw);
+      cur_lane = keep; }
     int pl = new_buf(hw / 2, F);
-    { Op o; o.kind = OP_POOL; o.in = x; o.out = V(pl); o.k = 3; h->ops.push_back(o); }
+    { Op o; o.kind = OP_POOL; o.lane = cur_lane; o.in = x; o.out = V(pl); o.k = 3; h->ops.push_back(o); }
     int low1 = new_buf(hw / 2, F);
     residual(p + "/lower1", V(pl), F, F, V(low1), hw / 2);
     int low2 = low1;
     if (n > 1) { low2 = new_buf(hw / 2, F); hourglass(name, n - 1, V(low1), V(low2), hw / 2); }
     int low3 = new_buf(hw / 2, F);
     residual(p + "/lower3", V(low2), F, F, V(low3), hw / 2);
-    { Op o; o.kind = OP_UPADD; o.in = V(up1); o.res = V(low3); o.out = dest; h->ops.push_back(o); }
+    { Op o; o.kind = OP_UPADD; o.lane = cur_lane; o.in = V(up1); o.res = V(low3); o.out = dest; h->ops.push_back(o); }
   }
   void build() {
     F = h->cfg.num_fea; J = h->cfg.num_jnt; S = h->cfg.num_stack;
@@ -224,13 +250,13 @@ struct Builder {
     conv_op(Lc1, V(h->buf_x0), V(c1));
     h->ops.back().need_dgrad = 0;
     int c2 = new_buf(IN / 2, 64);
-    residual("stem/conv_2", V(c1), 32, 64, V(c2), IN / 2);
+    residual("stem/conv_2", V(c1), 32, 64, V(c2), IN / 2, 2);
     int p1 = new_buf(OUT, 64);
-    { Op o; o.kind = OP_POOL; o.in = V(c2); o.out = V(p1); o.k = 2; h->ops.push_back(o); }
+    { Op o; o.kind = OP_POOL; o.lane = cur_lane; o.in = V(c2); o.out = V(p1); o.k = 2; h->ops.push_back(o); }
     int c3 = new_buf(OUT, 64);
     residual("stem/conv_3", V(p1), 64, 64, V(c3), OUT);
     int c4 = new_buf(OUT, F);
-    residual("stem/conv_4", V(c3), 64, F, V(c4), OUT);
+    residual("stem/conv_4", V(c3), 64, F, V(c4), OUT, 2);
     View hg_ins = V(c4);
     h->hg_ins0 = hg_ins;
     for (int s = 0; s < S; ++s) {
@@ -249,17 +275,19 @@ struct Builder {
       conv_op(add_layer(p + "/ll", 1, 1, F, F, 1, 1, 0.0005f, OUT), V(llr), ll);              // :128-131
       conv_op(add_layer(p + "/hm_out", 1, 1, F, J, 0, 0, 0.0005f, OUT), ll, hm);               // :133-135
       int h3 = new_buf(OUT, 128);
-      residual(p + "/hm3_res", V(lluvd), F + 3, 128, V(h3), OUT);            // :137-138
+      residual(p + "/hm3_res", V(lluvd), F + 3, 128, V(h3), OUT, 2);         // :137-138
       conv_op(add_layer(p + "/hm3_out", 1, 1, 128, J, 0, 0, 0.0005f, OUT), V(h3), hm3);        // :139-141
       int u1 = new_buf(OUT, 256);
-      residual(p + "/um_res1", cat, F + 2 * J, 256, V(u1), OUT);             // :143-144
+      residual(p + "/um_res1", cat, F + 2 * J, 256, V(u1), OUT, 2);          // :143-144
       int combin = new_buf(OUT, 512);
       residual(p + "/um_res2", V(u1), 256, 256, sub(combin, 0, 256), OUT);
       int catm = new_buf(OUT, F + 2 * J);
-      { Op o; o.kind = OP_MASKCOPY; o.in = cat; o.out = V(catm); h->ops.push_back(o); }      // :146-148
+      cur_lane = 1;                                                           // the masked branch runs next to the unmasked one
+      { Op o; o.kind = OP_MASKCOPY; o.lane = cur_lane; o.in = cat; o.out = V(catm); h->ops.push_back(o); }      // :146-148
       int m1 = new_buf(OUT, 256);
-      residual(p + "/um_mask_res1", V(catm), F + 2 * J, 256, V(m1), OUT);    // :149
+      residual(p + "/um_mask_res1", V(catm), F + 2 * J, 256, V(m1), OUT, 2);  // :149
       residual(p + "/um_mask_res2", V(m1), 256, 256, sub(combin, 256, 256), OUT);
+      cur_lane = 0;
       int combuvd = new_buf(OUT, 515);
       residual(p + "/um_comb", V(combin), 512, 512, sub(combuvd, 0, 512), OUT);   // :151-152
       h->uvd_dst.push_back(sub(combuvd, 512, 3));                              // :153
@@ -275,6 +303,65 @@ struct Builder {
       }
     }
     plan_backward();
+    plan_lanes();
+  }
+
+  // ---- lane hazard analysis ------------------------------------------------------------------------------------------------
+  struct Access { int pos, lane, buf, c0, c1; bool write; };
+  // order[pos] = op index; accesses(op, out): the views the op touches in this pass.  For every op: wait for the LATEST conflicting
+  // op (read-after-write, write-after-read, write-after-write on overlapping channel ranges of one buffer) of each other lane, unless
+  // this lane already waited for that op or a later one of the same lane (events of one stream are ordered).
+  template <class F>
+  void plan_pass(const std::vector<int>& order, F accesses, std::vector<OpPlan>& plan) {
+    plan.assign(h->ops.size(), OpPlan());
+    std::vector<std::vector<Access>> hist(2 * h->bufs.size());
+    int synced[kLanes][kLanes];
+    for (int a = 0; a < kLanes; ++a) for (int b = 0; b < kLanes; ++b) synced[a][b] = -1;
+    for (int pos = 0; pos < (int)order.size(); ++pos) {
+      const int oi = order[pos];
+      const int lane = h->ops[oi].lane;
+      std::vector<Access> acc;
+      accesses(h->ops[oi], acc);
+      int need[kLanes]; for (int l = 0; l < kLanes; ++l) need[l] = -1;
+      for (Access& a : acc) {
+        a.pos = pos; a.lane = lane;
+        for (const Access& q : hist[a.buf])
+          if (q.lane != lane && (a.write || q.write) && a.c0 < q.c1 && q.c0 < a.c1 && q.pos > need[q.lane]) need[q.lane] = q.pos;
+      }
+      OpPlan& pl = plan[oi];
+      for (int l = 0; l < kLanes; ++l)
+        if (l != lane && need[l] > synced[lane][l]) {
+          pl.wait_op[pl.nwait++] = order[need[l]];
+          plan[order[need[l]]].record = 1;
+          synced[lane][l] = need[l];
+        }
+      for (const Access& a : acc) hist[a.buf].push_back(a);
+    }
+  }
+  void plan_lanes() {
+    const int nb = (int)h->bufs.size();
+    auto rd = [](std::vector<Access>& v, int buf, const View& w) { if (w.buf >= 0) v.push_back(Access{0, 0, buf, w.coff, w.coff + w.C, false}); };
+    auto wr = [](std::vector<Access>& v, int buf, const View& w) { if (w.buf >= 0) v.push_back(Access{0, 0, buf, w.coff, w.coff + w.C, true}); };
+    std::vector<int> fo(h->ops.size()), bo(h->ops.size());
+    for (size_t i = 0; i < h->ops.size(); ++i) { fo[i] = (int)i; bo[i] = (int)(h->ops.size() - 1 - i); }
+    // forward: activation arena (buffer ids as they are)
+    plan_pass(fo, [&](const Op& o, std::vector<Access>& v) {
+      rd(v, o.in.buf, o.in);
+      if (o.res.buf >= 0) rd(v, o.res.buf, o.res);
+      wr(v, o.out.buf, o.out);                                   // also covers `accumulate` (read-modify-write)
+      if (o.raw >= 0) { View r; r.buf = o.raw; r.coff = 0; r.C = h->bufs[o.raw].Cs; wr(v, o.raw, r); }
+    }, h->plan_fwd);
+    // backward: gradient arena (buffer id + nb); forward activations are read-only here and complete before the pass starts
+    plan_pass(bo, [&](const Op& o, std::vector<Access>& v) {
+      rd(v, nb + o.out.buf, o.out);
+      if (o.kind == OP_CONV) {
+        if (o.res.buf >= 0) wr(v, nb + o.res.buf, o.res);
+        if (o.need_dgrad) wr(v, nb + o.in.buf, o.in);
+      } else {
+        wr(v, nb + o.in.buf, o.in);
+        if (o.kind == OP_UPADD) wr(v, nb + o.res.buf, o.res);
+      }
+    }, h->plan_bwd);
   }
 
   // decide overwrite / accumulate for each gradient write of the reverse schedule
@@ -540,6 +627,7 @@ int ensure_workspace(dr_handle* h, int B, bool train) {
     if (h->side_stream) {
       CUDA_TRY(h, cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));
       for (int i = 0; i < dr_handle::kScratchSlots; ++i) {
+        if (h->ev_ready[i]) continue;
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wdone[i], cudaEventDisableTiming));
       }
@@ -551,11 +639,64 @@ int ensure_workspace(dr_handle* h, int B, bool train) {
   return DR_OK;
 }
 
+// run-time side of the lane plan (OpPlan): which stream an op runs on, the event waits before it, the event record after it
+struct LaneCtx {
+  dr_handle* h; cudaStream_t st; bool on; const std::vector<OpPlan>* plan; std::vector<cudaEvent_t>* ev;
+  bool started[kLanes];
+  int begin() {                       // everything enqueued on `st` so far (inputs, memsets, previous passes) precedes every lane
+    for (int l = 0; l < kLanes; ++l) started[l] = false;
+    started[0] = true;
+    if (on) CUDA_TRY(h, cudaEventRecord(h->ev_pass_start, st));
+    return DR_OK;
+  }
+  cudaStream_t stream(int lane) const { return (on && lane > 0) ? h->lane_stream[lane] : st; }
+  int enter(int oi, cudaStream_t* out) {
+    const int lane = on ? h->ops[oi].lane : 0;
+    cudaStream_t s = stream(lane);
+    if (on) {
+      if (!started[lane]) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_pass_start, 0)); started[lane] = true; }
+      const OpPlan& pl = (*plan)[oi];
+      for (int i = 0; i < pl.nwait; ++i) CUDA_TRY(h, cudaStreamWaitEvent(s, (*ev)[pl.wait_op[i]], 0));
+    }
+    *out = s;
+    return DR_OK;
+  }
+  int leave(int oi) {
+    if (on && (*plan)[oi].record) CUDA_TRY(h, cudaEventRecord((*ev)[oi], stream(h->ops[oi].lane)));
+    return DR_OK;
+  }
+  int join() {                        // the caller's stream continues only after every lane has drained
+    if (!on) return DR_OK;
+    for (int l = 1; l < kLanes; ++l)
+      if (started[l]) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_lane_done[l], h->lane_stream[l]));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_lane_done[l], 0));
+      }
+    return DR_OK;
+  }
+};
+
+int ensure_lanes(dr_handle* h) {
+  if (!h->lanes_on || h->ev_pass_start) return DR_OK;
+  for (int l = 1; l < kLanes; ++l) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+  for (int l = 0; l < kLanes; ++l) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lane_done[l], cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pass_start, cudaEventDisableTiming));
+  h->ev_fwd.assign(h->ops.size(), nullptr); h->ev_bwd.assign(h->ops.size(), nullptr);
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    if (h->plan_fwd[i].record) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fwd[i], cudaEventDisableTiming));
+    if (h->plan_bwd[i].record) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bwd[i], cudaEventDisableTiming));
+  }
+  return DR_OK;
+}
+
 int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int training, int update_state,
-                 uint64_t dropout_seed, cudaStream_t st) {
+                 uint64_t dropout_seed, cudaStream_t st0) {
   if (!h->params || !h->state) return fail(h, DR_ERR_STATE, "dr_bind() not called");
   int rc = ensure_workspace(h, B, training != 0);
   if (rc) return rc;
+  rc = ensure_lanes(h);
+  if (rc) return rc;
+  cudaStream_t st = st0;
   Exec X{h, B, st};
   const int IN = h->cfg.in_hw, OUT = h->cfg.out_hw;
   int nl = 0;
@@ -574,8 +715,13 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
   } else {
     fold_all_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state, h->aff); ++nl;
   }
+  LaneCtx lanes{h, st0, h->lanes_on, &h->plan_fwd, &h->ev_fwd, {}};
+  rc = lanes.begin();
+  if (rc) return rc;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const Op& o = h->ops[oi];
+    rc = lanes.enter((int)oi, &st);          // `st` = this op's lane stream from here on
+    if (rc) return rc;
     switch (o.kind) {
       case OP_CONV: {
         const Layer& L = h->layers[o.layer];
@@ -584,7 +730,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
         p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         set_fwd_weights(h, L, h->precision, p);
-        p.chunk_kb = training ? h->chunk_train : h->chunk_eval;
+        p.chunk_kb = training ? h->chunk_train : h->chunk_eval; p.chunk_min_kb = h->chunk_min_kb;
         const float* aff = h->aff + L.aff_off;
         const float* res = o.res.buf >= 0 ? X.ptr(o.res) : nullptr;
         const int res_cs = o.res.buf >= 0 ? X.cs(o.res) : 0;
@@ -626,13 +772,18 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         nl += launch_copy_view(X.npix(o.in), o.in.C, X.ptr(o.in), X.cs(o.in), X.ptr(o.out), X.cs(o.out), 0, tiny, st);
         break;
     }
+    rc = lanes.leave((int)oi);
+    if (rc) return rc;
   }
+  rc = lanes.join();
+  if (rc) return rc;
   h->launches += nl;
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;
 }
 
-int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st);   // NCCL all-reduce of grads[lo,hi) (defined with the communicator below)
+struct LaneCtx;
+int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st, LaneCtx* lanes);   // NCCL all-reduce of grads[lo,hi) (defined with the communicator below)
 
 int apply_fills(dr_handle* h, Exec& X, const GradWrite& g, cudaStream_t st) {
   int nl = 0;
@@ -640,8 +791,9 @@ int apply_fills(dr_handle* h, Exec& X, const GradWrite& g, cudaStream_t st) {
   return nl;
 }
 
-int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, const float* coms, float* loss_out, cudaStream_t st) {
+int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, const float* coms, float* loss_out, cudaStream_t st0) {
   if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
+  cudaStream_t st = st0;
   Exec X{h, B, st};
   int nl = 0;
   const int OUT = h->cfg.out_hw, J = h->cfg.num_jnt, S = h->cfg.num_stack;
@@ -660,7 +812,9 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   nl += launch_wd(h->n_params, h->params, h->wdmask, h->grads, h->loss_acc + 3, st);
   if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
 
-  int conv_idx = 0;
+  int lane_convs[kLanes] = {};
+  LaneCtx lanes{h, st0, h->lanes_on, &h->plan_bwd, &h->ev_bwd, {}};
+  { int rc = lanes.begin(); if (rc) return rc; }
   const bool overlap = h->overlap_armed && h->nccl_comm && h->comm_world > 1;
   size_t next_bucket = 0;
   h->overlap_armed = false;
@@ -668,11 +822,12 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
     const Op& o = h->ops[oi];
     if (overlap) {           // every bucket whose last contributing op (in this reverse walk) lies behind us is final: reduce it now
       while (next_bucket < h->buckets.size() && h->buckets[next_bucket].first_op > oi) {
-        int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st);
+        int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st0, &lanes);
         if (rc) return rc;
         ++next_bucket;
       }
     }
+    { int rc = lanes.enter(oi, &st); if (rc) return rc; }          // `st` = this op's lane stream from here on
     switch (o.kind) {
       case OP_CONV: {
         const Layer& L = h->layers[o.layer];
@@ -682,7 +837,8 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           nl += apply_fills(h, X, o.gw_res, st);
           nl += launch_copy_view(np, o.res.C, dy, dy_cs, X.gptr(o.res), X.cs(o.res), o.gw_res.acc, nullptr, st);
         }
-        const int slot = conv_idx % dr_handle::kScratchSlots; ++conv_idx;
+        const int ln = lanes.on ? o.lane : 0;                         // d(raw) scratch slots are per lane (each lane cycles through three)
+        const int slot = ln * dr_handle::kSlotsPerLane + lane_convs[ln] % dr_handle::kSlotsPerLane; ++lane_convs[ln];
         float* dz = h->scratch + (size_t)slot * h->scratch_per_crop * h->cap_B; const int dz_cs = (L.cout + 3) / 4 * 4;
         if (h->side_stream) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_wdone[slot], 0));   // the wgrad that last read this slot is done
         if (L.brn) {
@@ -714,7 +870,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin; p.k = L.k; p.stride = 1;
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
           set_dgrad_weights(h, L, h->precision, p);
-          p.chunk_kb = h->chunk_train;
+          p.chunk_kb = h->chunk_train; p.chunk_min_kb = h->chunk_min_kb;
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
           RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
@@ -741,10 +897,13 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
                                X.ptr(X.whole(h->buf_tiny)), st);
         break;
     }
+    { int rc = lanes.leave(oi); if (rc) return rc; }
   }
+  { int rc = lanes.join(); if (rc) return rc; }
+  st = st0;
   if (overlap) {
     while (next_bucket < h->buckets.size()) {
-      int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st);
+      int rc = reduce_range(h, h->buckets[next_bucket].lo, h->buckets[next_bucket].hi, st0, nullptr);
       if (rc) return rc;
       ++next_bucket;
     }
@@ -827,10 +986,16 @@ void plan_buckets(dr_handle* h, int nbuckets) {
 }
 
 // all-reduce(sum) of grads[lo,hi) on the communication stream, after everything enqueued so far on `st` and on the wgrad stream
-int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st) {
+int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st, LaneCtx* lanes) {
   NcclApi& a = nccl_api();
   CUDA_TRY(h, cudaEventRecord(h->ev_bucket_main, st));
   CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_main, 0));
+  if (lanes && lanes->on)                                   // bias / BRN parameter gradients are written on the lane streams
+    for (int l = 1; l < kLanes; ++l)
+      if (lanes->started[l]) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_lane_done[l], h->lane_stream[l]));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_lane_done[l], 0));
+      }
   if (h->side_stream && h->wgrad_stream) {
     CUDA_TRY(h, cudaEventRecord(h->ev_bucket_side, h->wgrad_stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_side, 0));
@@ -890,12 +1055,25 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   // CTA-pair (cta_group::2) 3xTF32 kernel for the big layers: on by default; dr_config.reserved[1] < 0 or DENSEREG_TC_PAIR=0 turns it off
   { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] >= 0 && !(env && env[0] == '0'); }
   { const char* env = getenv("DENSEREG_PREP_ONCE"); h->prep_once = !(env && env[0] == '0'); }
+  { const char* env = getenv("DENSEREG_LANES"); h->lanes_on = !(env && env[0] == '0'); }
   { const char* e = getenv("DENSEREG_TC_CHUNK"); if (e) { h->chunk_eval = h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; } }
   { const char* e = getenv("DENSEREG_TC_CHUNK_EVAL"); if (e) h->chunk_eval = atoi(e) > 0 ? atoi(e) : 0; }
   { const char* e = getenv("DENSEREG_TC_CHUNK_TRAIN"); if (e) h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; }
+  { const char* e = getenv("DENSEREG_TC_CHUNK_MINKB"); if (e) h->chunk_min_kb = atoi(e) > 0 ? atoi(e) : 0; }
   Builder b{h, 0, 0, 0};
   b.build();
-  if (b.plan_overflow) { delete h; return DR_ERR_UNSUPPORTED; }   // a gradient view with > 4 unwritten channel gaps (never on um_v1)
+  if (b.plan_overflow) { delete h; return DR_ERR_UNSUPPORTED; }
+  if (getenv("DENSEREG_DUMP_PLAN")) {                   // debug: the lane plan (op, lane, waits, record) of both passes
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+      const Op& o = h->ops[i];
+      const char* kind = o.kind == OP_CONV ? "conv" : o.kind == OP_POOL ? "pool" : o.kind == OP_UPADD ? "upadd" : "maskcopy";
+      fprintf(stderr, "PLAN %3zu %-8s %-24s lane %d | fwd wait", i, kind, o.kind == OP_CONV ? h->layers[o.layer].name : "", o.lane);
+      for (int k = 0; k < h->plan_fwd[i].nwait; ++k) fprintf(stderr, " %d", h->plan_fwd[i].wait_op[k]);
+      fprintf(stderr, " rec %d | bwd wait", h->plan_fwd[i].record);
+      for (int k = 0; k < h->plan_bwd[i].nwait; ++k) fprintf(stderr, " %d", h->plan_bwd[i].wait_op[k]);
+      fprintf(stderr, " rec %d\n", h->plan_bwd[i].record);
+    }
+  }   // a gradient view with > 4 unwritten channel gaps (never on um_v1)
   *out = h;
   return DR_OK;
 }
@@ -910,7 +1088,12 @@ int dr_destroy(dr_handle* h) {
   if (h->infer_graph.exec) cudaGraphExecDestroy(h->infer_graph.exec);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
-  for (int i = 0; i < 3; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_wdone[i]) cudaEventDestroy(h->ev_wdone[i]); }
+  for (int i = 0; i < dr_handle::kScratchSlots; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_wdone[i]) cudaEventDestroy(h->ev_wdone[i]); }
+  for (int l = 1; l < kLanes; ++l) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+  for (int l = 0; l < kLanes; ++l) if (h->ev_lane_done[l]) cudaEventDestroy(h->ev_lane_done[l]);
+  if (h->ev_pass_start) cudaEventDestroy(h->ev_pass_start);
+  for (cudaEvent_t e : h->ev_fwd) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_bwd) if (e) cudaEventDestroy(e);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->act); cudaFree(h->gact); cudaFree(h->rawa); cudaFree(h->scratch); cudaFree(h->aff); cudaFree(h->bstat);
   cudaFree(h->wk); cudaFree(h->wa); cudaFree(h->wk_hi); cudaFree(h->wk_lo); cudaFree(h->wa_hi); cudaFree(h->wa_lo); cudaFree(h->wdmask); cudaFree(h->sums); cudaFree(h->sums_bw); cudaFree(h->loss_acc);
@@ -1150,7 +1333,7 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
   if (h->nccl_comm && h->comm_world > 1) {
     if (world != h->comm_world) return fail(h, DR_ERR_ARG, "dr_optimizer_step: world differs from the communicator's size");
     if (!h->reduced_in_backward) {                          // not overlapped with the last backward: one all-reduce of the whole buffer now
-      int rc = reduce_range(h, 0, (int64_t)h->n_params, ost);
+      int rc = reduce_range(h, 0, (int64_t)h->n_params, ost, nullptr);
       if (rc) return rc;
       CUDA_TRY(h, cudaEventRecord(h->ev_comm_done, h->comm_stream));
     }
@@ -1220,7 +1403,7 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
   if (precision != DR_PREC_FP32 && !reuse) { int rc = ensure_prepped(h, precision, (cudaStream_t)stream); if (rc) return rc; }
   set_fwd_weights(h, L, precision, p); p.y = y; p.y_cs = L.cout; p.pair = force_pair ? 2 : 0;
-  p.chunk_kb = (precision_flags & 0x400) ? h->chunk_eval : 0;          // debug flag 0x400: two-level accumulation as in inference
+  p.chunk_kb = (precision_flags & 0x400) ? h->chunk_eval : 0; p.chunk_min_kb = h->chunk_min_kb;          // debug flag 0x400: two-level accumulation as in inference
   { int64_t nl = 0; RUN_TRY(nl, run_conv(h, p, precision, (cudaStream_t)stream)); h->launches += nl; }
   CUDA_TRY(h, cudaGetLastError());
   return DR_OK;

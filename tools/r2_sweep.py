@@ -5,21 +5,15 @@ Each child checks the training micro-step against the fp32 FFMA engine (GPU vs G
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
-CONFIGS = [   # round-2 second pass: defaults now = wgrad swap + 1 wave, BRN reduce 148 blocks, float4 pool backward, per-CTA BRN statistics
+CONFIGS = [   # round-2 third pass: lanes (multi-stream op scheduling) on top of the adopted defaults
     ("base", {}),
+    ("no_lanes", {"DENSEREG_LANES": "0"}),
+    ("no_lanes_no_side", {"DENSEREG_LANES": "0", "DENSEREG_SIDE_STREAM": "0"}),
+    ("lanes_no_side", {"DENSEREG_SIDE_STREAM": "0"}),
     ("wgrad_w2", {"DENSEREG_WGRAD_WAVES": "2"}),
     ("wgrad_a_tmem", {"DENSEREG_WGRAD_A_TMEM": "1"}),
-    ("wgrad_a_tmem_w2", {"DENSEREG_WGRAD_A_TMEM": "1", "DENSEREG_WGRAD_WAVES": "2"}),
-    ("wgrad_a_tmem_w3", {"DENSEREG_WGRAD_A_TMEM": "1", "DENSEREG_WGRAD_WAVES": "3"}),
-    ("wgrad_a_tmem_swap2", {"DENSEREG_WGRAD_A_TMEM": "1", "DENSEREG_WGRAD_SWAP": "2"}),
-    ("a_tmem_1", {"DENSEREG_TC_A_TMEM": "1"}),
-    ("a_tmem_1_wgrad_a_tmem", {"DENSEREG_TC_A_TMEM": "1", "DENSEREG_WGRAD_A_TMEM": "1"}),
-    ("a_tmem_1_wgrad_a_tmem_w2", {"DENSEREG_TC_A_TMEM": "1", "DENSEREG_WGRAD_A_TMEM": "1", "DENSEREG_WGRAD_WAVES": "2"}),
-    ("chunk1", {"DENSEREG_TC_CHUNK": "1"}),
-    ("chunk2", {"DENSEREG_TC_CHUNK": "2"}),
-    ("chunk4", {"DENSEREG_TC_CHUNK": "4"}),
-    ("no_stats_per_cta", {"DENSEREG_TC_STATS_PER_CTA": "0"}),
-    ("brn_blocks_74", {"DENSEREG_BRN_BLOCKS": "74"}),
+    ("a_tmem_0", {"DENSEREG_TC_A_TMEM": "0"}),
+    ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
 ]
 want = set(sys.argv[1:])
 path = os.path.join(OUT, "r2_sweep.jsonl")
