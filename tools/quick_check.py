@@ -83,6 +83,11 @@ try:
     for r in eng.trace_records():
         c = cls.setdefault(r["kind"] + ":" + r["kernel"], [0, 0.0]); c[0] += 1; c[1] += r["ms"]
     eng.trace(False)
+    lay = {}
+    for r in eng.trace_records():
+        k = "%s hw%d k%d %d->%d %s" % (r["kind"], r["hw"], r["k"], r["cin"], r["cout"], r["kernel"])
+        c = lay.setdefault(k, [0, 0.0, 2.0 * r["B"] * r["hw"] ** 2 * r["k"] ** 2 * r["cin"] * r["cout"]]); c[0] += 1; c[1] += r["ms"]
+    out["trace_layers"] = [[k, v[0], round(v[1], 4), round(v[2] * v[0] / max(v[1], 1e-9) / 1e9, 1)] for k, v in sorted(lay.items(), key=lambda kv: -kv[1][1])[:60]]
     out["trace_ms"] = {k: [v[0], round(v[1], 3)] for k, v in sorted(cls.items())}
     out["cpu_enqueue_one_micro_ms"] = t_one * 1e3
     out.update(ms_per_micro=ms, crops_per_s=B / ms * 1e3, launches_per_micro=(eng.launch_count - l0) / (reps * a.micro),
