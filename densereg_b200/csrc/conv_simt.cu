@@ -285,9 +285,11 @@ int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st) {
   const int M = p.B * p.Ho * p.Wo;
   const int K = p.k * p.k * p.Cin;
   const int gx = (K + WK - 1) / WK, gy = (p.Cout + WN - 1) / WN;
-  // enough M-splits to fill the 148 SMs a few times over, at least 512 pixels per block
+  // enough M-splits to fill the 148 SMs a few times over, at least 64 pixels (4 tiles of WM) per block.  (512 pixels per block left the
+  // 4x4 / 2x2 hourglass levels -- 640 / 160 pixels at batch 40 -- on 2 blocks walking 20 tiles each: 35 us per launch, 18 launches per
+  // micro-batch; profiles/r2_sweep.md)
   int splits = (148 * 4 + gx * gy - 1) / (gx * gy);
-  int max_splits = (M + 511) / 512;
+  int max_splits = (M + 63) / 64;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int m_per_block = ((M + splits - 1) / splits + WM - 1) / WM * WM;

@@ -27,6 +27,7 @@ published constants (magic, masked CRC-32C, varint coding) and by a writer/reade
 pyarrow's snappy codec.  Host-side byte plumbing only.
 """
 import os
+import re
 import struct
 
 import numpy as np
@@ -302,13 +303,43 @@ _OPTIONAL_SUFFIXES = ("/biased", "/local_step", "/r_max", "/d_max", "/curr_t")
 
 
 def _lookup(tensors, name):
-    """Exact name, else the same variable without the doubled zero-debias scope ('<conv>/BatchReNorm/moving_mean/biased')."""
-    if name in tensors:
-        return tensors[name]
+    """Exact name, else the same variable without the doubled zero-debias scope ('<conv>/BatchReNorm/moving_mean/biased'), else either
+    form under stock slim's scope name 'BatchNorm' (the reference's fork opens 'BatchReNorm', network/slim/ops.py:81)."""
+    cands = [name]
     parts = name.split("/BatchReNorm/")
     if len(parts) == 3:
-        return tensors.get(parts[0] + "/BatchReNorm/" + parts[2])
+        cands.append(parts[0] + "/BatchReNorm/" + parts[2])
+    cands += [c.replace("BatchReNorm", "BatchNorm") for c in list(cands)]
+    for c in cands:
+        if c in tensors:
+            return tensors[c]
     return None
+
+
+def _scope_index(scope):
+    """'hg_imgproc/Conv_12' -> ('hg_imgproc', 12); 'Conv' -> ('', 0): creation order of slim's auto-numbered conv scopes."""
+    head, _, leaf = scope.rpartition("/")
+    m = re.match(r"^(.*?)(?:_(\d+))?$", leaf)
+    return head, int(m.group(2) or 0)
+
+
+def remap_conv_scopes(tensors, layers):
+    """Tolerant matching for checkpoints whose conv scopes are not the ones tf_scopes() predicts (another enclosing scope, or one flat
+    numbering): order the checkpoint's '<scope>/weights' tensors by creation order (scope prefix in order of first appearance of the
+    stem, then the auto-number) and accept the renaming only if the whole sequence of HWIO shapes equals this network's.  Returns
+    {predicted scope: checkpoint scope} or None."""
+    keys = [k[:-len("/weights")] for k, v in tensors.items() if k.endswith("/weights") and np.asarray(v).ndim == 4]
+    if len(keys) != len(layers):
+        return None
+    def order(scope):
+        head, idx = _scope_index(scope)
+        return (0 if "imgproc" in head else 1, head, idx)       # the stem scope ('hg_imgproc', um_v1.py:84) is created first
+    keys.sort(key=order)
+    pred = tf_scopes(layers)
+    for L, k in zip(layers, keys):
+        if tuple(np.asarray(tensors[k + "/weights"]).shape) != (L["k"], L["k"], L["cin"], L["cout"]):
+            return None
+    return dict(zip(pred, keys))
 
 
 def load_into_flat(tensors, layers, n_params, n_state, strict=True):
@@ -318,7 +349,19 @@ def load_into_flat(tensors, layers, n_params, n_state, strict=True):
     params = np.zeros(n_params, np.float32); state = np.zeros(n_state, np.float32)
     adam_m = np.zeros(n_params, np.float32); adam_v = np.zeros(n_params, np.float32)
     have_adam, missing = True, []
-    for name, buf, off, shape in variable_map(layers):
+    vmap = variable_map(layers)
+    if any(_lookup(tensors, name) is None for name, _, _, _ in vmap if name.endswith("/weights")):
+        ren = remap_conv_scopes(tensors, layers)                  # predicted scope names absent: try creation order + shapes
+        if ren:
+            def renamed(name):
+                for a, b in ren.items():
+                    if name == a or name.startswith(a + "/"):
+                        return (b + name[len(a):]).replace("/" + a + "/", "/" + b + "/")
+                return name
+            # longest scope first so that 'Conv_1' is not taken for a prefix of 'Conv_12'
+            ren = dict(sorted(ren.items(), key=lambda kv: -len(kv[0])))
+            vmap = [(renamed(name), buf, off, shape) for name, buf, off, shape in vmap]
+    for name, buf, off, shape in vmap:
         n = int(np.prod(shape, dtype=np.int64))
         t = _lookup(tensors, name)
         if t is None:
@@ -341,7 +384,9 @@ def load_into_flat(tensors, layers, n_params, n_state, strict=True):
                 adam_m[off:off + n] = np.asarray(m, np.float32).reshape(-1)
                 adam_v[off:off + n] = np.asarray(v, np.float32).reshape(-1)
     if missing and strict:
-        raise CheckpointError("checkpoint lacks %d variable(s) of this network, first: %s" % (len(missing), missing[0]))
+        have = sorted(k for k in tensors if "/Adam" not in k)
+        raise CheckpointError("checkpoint lacks %d variable(s) of this network, first: %s\ncheckpoint holds %d variables, e.g.:\n  %s"
+                              % (len(missing), missing[0], len(have), "\n  ".join(have[:40])))
     step = int(np.asarray(tensors["global_step"]).reshape(-1)[0]) if "global_step" in tensors else 0
     return params, state, (adam_m if have_adam else None), (adam_v if have_adam else None), step
 

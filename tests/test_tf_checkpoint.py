@@ -133,8 +133,38 @@ def test_export_import_roundtrip(tmp_path):
     with pytest.raises(T.CheckpointError):
         T.load_into_flat(tensors, other, np2, ns2)
     del slim["Conv_5/weights"]
-    with pytest.raises(T.CheckpointError):
+    with pytest.raises(T.CheckpointError) as ei:
         T.load_into_flat(slim, layers, n_params, n_state)
+    assert "checkpoint holds" in str(ei.value) and "Conv_15/weights" in str(ei.value)    # the failure lists what the file does contain
+
+
+def test_tolerant_name_matching(tmp_path):
+    """pretrained bundles may use stock slim's 'BatchNorm' scope, or conv scopes under another enclosing scope / one flat numbering.
+    Both are matched (the second by creation order + the full sequence of HWIO shapes); anything else still fails loudly."""
+    layers, n_params, n_state = _layers(1, 64, 16)
+    rng = np.random.RandomState(5)
+    params = rng.randn(n_params).astype(np.float32); state = rng.rand(n_state).astype(np.float32)
+    tensors = T.flat_to_tensors(layers, params, state)
+    bn = {k.replace("BatchReNorm", "BatchNorm"): v for k, v in tensors.items()}
+    p2, s2, *_ = T.load_into_flat(bn, layers, n_params, n_state)
+    assert np.array_equal(p2, params) and np.array_equal(s2, state)
+    # every conv under one enclosing scope with one flat numbering: tower/Conv, tower/Conv_1, ... (stem first)
+    scopes = T.tf_scopes(layers)
+    flat = {}
+    for k, v in tensors.items():
+        for i, sc in sorted(enumerate(scopes), key=lambda t: -len(t[1])):
+            if k == sc or k.startswith(sc + "/"):
+                new = "tower/Conv" + ("_%d" % i if i else "")
+                flat[(new + k[len(sc):]).replace("/" + sc + "/", "/" + new + "/")] = v
+                break
+        else:
+            flat[k] = v
+    assert "tower/Conv_3/weights" in flat and "Conv_3/weights" not in flat
+    p3, s3, *_ = T.load_into_flat(flat, layers, n_params, n_state)
+    assert np.array_equal(p3, params) and np.array_equal(s3, state)
+    flat["tower/Conv_7/weights"] = flat["tower/Conv_7/weights"][..., :-1]                  # one shape off -> no renaming, loud failure
+    with pytest.raises(T.CheckpointError):
+        T.load_into_flat(flat, layers, n_params, n_state)
 
 
 @pytest.mark.gpu
