@@ -101,8 +101,9 @@ struct dr_handle {
   // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
   static const int kSlotsPerLane = 3;
   static const int kScratchSlots = kSlotsPerLane * kLanes;
-  cudaStream_t wgrad_stream = nullptr;
-  cudaEvent_t ev_ready[kSlotsPerLane * kLanes] = {}, ev_wdone[kSlotsPerLane * kLanes] = {}, ev_join = nullptr;
+  cudaStream_t wgrad_stream = nullptr, wgrad_stream2 = nullptr;   // filter gradients alternate between two side streams (DENSEREG_WGRAD_STREAMS=1: one)
+  int wgrad_streams = 2;
+  cudaEvent_t ev_ready[kSlotsPerLane * kLanes] = {}, ev_wdone[kSlotsPerLane * kLanes] = {}, ev_join = nullptr, ev_join2 = nullptr;
   // lanes (see OpPlan): lane 0 is the caller's stream
   bool lanes_on = true;
   cudaStream_t lane_stream[kLanes] = {};
@@ -121,7 +122,7 @@ struct dr_handle {
   // buckets on `comm_stream` while the backward pass of the step's LAST micro-batch is still running (dr_comm_overlap_next_backward)
   void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_bucket_main = nullptr, ev_bucket_side = nullptr, ev_comm_done = nullptr;
+  cudaEvent_t ev_bucket_main = nullptr, ev_bucket_side = nullptr, ev_bucket_side2 = nullptr, ev_comm_done = nullptr;
   struct Bucket { int64_t lo, hi; int first_op; };       // flat range [lo,hi) is final once the reverse walk has finished op `first_op`
   std::vector<Bucket> buckets;
   bool overlap_armed = false, reduced_in_backward = false;
@@ -626,12 +627,15 @@ int ensure_workspace(dr_handle* h, int B, bool train) {
     { const char* env = getenv("DENSEREG_SIDE_STREAM"); h->side_stream = !(env && env[0] == '0'); }
     if (h->side_stream) {
       CUDA_TRY(h, cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&h->wgrad_stream2, cudaStreamNonBlocking));
+      { const char* e = getenv("DENSEREG_WGRAD_STREAMS"); h->wgrad_streams = (e && e[0] == '1') ? 1 : 2; }
       for (int i = 0; i < dr_handle::kScratchSlots; ++i) {
         if (h->ev_ready[i]) continue;
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wdone[i], cudaEventDisableTiming));
       }
       CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     }
     h->cap_train = true;
   }
@@ -813,6 +817,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
 
   int lane_convs[kLanes] = {};
+  int wgrad_count = 0;
   LaneCtx lanes{h, st0, h->lanes_on, &h->plan_bwd, &h->ev_bwd, {}};
   { int rc = lanes.begin(); if (rc) return rc; }
   const bool overlap = h->overlap_armed && h->nccl_comm && h->comm_world > 1;
@@ -856,10 +861,11 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         wp.k = L.k; wp.stride = L.stride; wp.pad_t = wp.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         wp.dw = h->grads + L.w_off;
         if (h->side_stream) {
+          cudaStream_t ws = (h->wgrad_streams > 1 && (wgrad_count++ & 1)) ? h->wgrad_stream2 : h->wgrad_stream;
           CUDA_TRY(h, cudaEventRecord(h->ev_ready[slot], st));
-          CUDA_TRY(h, cudaStreamWaitEvent(h->wgrad_stream, h->ev_ready[slot], 0));
-          RUN_TRY(nl, run_wgrad(h, wp, h->precision, h->wgrad_stream));
-          CUDA_TRY(h, cudaEventRecord(h->ev_wdone[slot], h->wgrad_stream));
+          CUDA_TRY(h, cudaStreamWaitEvent(ws, h->ev_ready[slot], 0));
+          RUN_TRY(nl, run_wgrad(h, wp, h->precision, ws));
+          CUDA_TRY(h, cudaEventRecord(h->ev_wdone[slot], ws));
         } else {
           RUN_TRY(nl, run_wgrad(h, wp, h->precision, st));
         }
@@ -913,6 +919,8 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   if (h->side_stream) {          // the optimiser step / next micro-batch on `st` must see every filter gradient
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->wgrad_stream));
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    CUDA_TRY(h, cudaEventRecord(h->ev_join2, h->wgrad_stream2));
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
   }
   h->launches += nl;
   CUDA_TRY(h, cudaGetLastError());
@@ -999,6 +1007,8 @@ int reduce_range(dr_handle* h, int64_t lo, int64_t hi, cudaStream_t st, LaneCtx*
   if (h->side_stream && h->wgrad_stream) {
     CUDA_TRY(h, cudaEventRecord(h->ev_bucket_side, h->wgrad_stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_side, 0));
+    CUDA_TRY(h, cudaEventRecord(h->ev_bucket_side2, h->wgrad_stream2));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_bucket_side2, 0));
   }
   const int rc = a.all_reduce(h->grads + lo, h->grads + lo, (size_t)(hi - lo), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, h->comm_stream);
   if (rc != 0) return nccl_fail(h, "ncclAllReduce", rc);
@@ -1084,10 +1094,13 @@ int dr_destroy(dr_handle* h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_bucket_main) cudaEventDestroy(h->ev_bucket_main);
   if (h->ev_bucket_side) cudaEventDestroy(h->ev_bucket_side);
+  if (h->ev_bucket_side2) cudaEventDestroy(h->ev_bucket_side2);
   if (h->ev_comm_done) cudaEventDestroy(h->ev_comm_done);
   if (h->infer_graph.exec) cudaGraphExecDestroy(h->infer_graph.exec);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
+  if (h->wgrad_stream2) cudaStreamDestroy(h->wgrad_stream2);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   for (int i = 0; i < dr_handle::kScratchSlots; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_wdone[i]) cudaEventDestroy(h->ev_wdone[i]); }
   for (int l = 1; l < kLanes; ++l) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
   for (int l = 0; l < kLanes; ++l) if (h->ev_lane_done[l]) cudaEventDestroy(h->ev_lane_done[l]);
@@ -1305,6 +1318,7 @@ int dr_comm_init(dr_handle* h, int rank, int world, const void* nccl_unique_id12
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bucket_main, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bucket_side, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_bucket_side2, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming));
   int nb = 4; { const char* e = getenv("DENSEREG_COMM_BUCKETS"); if (e && atoi(e) > 0) nb = atoi(e); }
   plan_buckets(h, nb);
