@@ -24,6 +24,14 @@ class DrLayerInfo(C.Structure):
                 ("in_hw", C.c_int32), ("out_hw", C.c_int32)]
 
 
+class DrOpInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("lane", C.c_int32), ("layer", C.c_int32), ("need_dgrad", C.c_int32), ("raw_buf", C.c_int32),
+                ("in_buf", C.c_int32), ("in_c0", C.c_int32), ("in_c", C.c_int32),
+                ("out_buf", C.c_int32), ("out_c0", C.c_int32), ("out_c", C.c_int32),
+                ("res_buf", C.c_int32), ("res_c0", C.c_int32), ("res_c", C.c_int32),
+                ("nwait", C.c_int32 * 2), ("wait_op", (C.c_int32 * 3) * 2), ("record", C.c_int32 * 2)]
+
+
 class DrTraceRec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("B", C.c_int32), ("hw", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("kernel", C.c_int32), ("ms", C.c_float)]
@@ -62,6 +70,8 @@ SIGNATURES = {
     "dr_debug_conv": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, C.c_int, _P]),
     "dr_debug_conv_bwd": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, C.c_int, _P]),
     "dr_debug_get_output": (C.c_int, [_P, C.c_int, C.c_int, _F, C.c_int, _P]),
+    "dr_num_ops": (C.c_int, [_P]),
+    "dr_debug_op": (C.c_int, [_P, C.c_int, C.POINTER(DrOpInfo)]),
     "dr_trace": (C.c_int, [_P, C.c_int]),
     "dr_trace_count": (C.c_int, [_P]),
     "dr_trace_get": (C.c_int, [_P, C.c_int, C.POINTER(DrTraceRec)]),

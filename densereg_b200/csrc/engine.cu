@@ -1146,6 +1146,23 @@ int dr_trace_get(const dr_handle* h, int idx, dr_trace_rec* out) {
   return DR_OK;
 }
 
+int dr_num_ops(const dr_handle* h) { return h ? (int)h->ops.size() : 0; }
+int dr_debug_op(const dr_handle* h, int idx, dr_op_info* out) {
+  if (!h || !out || idx < 0 || idx >= (int)h->ops.size()) return DR_ERR_ARG;
+  const Op& o = h->ops[idx];
+  memset(out, 0, sizeof(*out));
+  out->kind = (int32_t)o.kind; out->lane = o.lane; out->layer = o.layer; out->need_dgrad = o.need_dgrad; out->raw_buf = o.raw;
+  out->in_buf = o.in.buf; out->in_c0 = o.in.coff; out->in_c = o.in.C;
+  out->out_buf = o.out.buf; out->out_c0 = o.out.coff; out->out_c = o.out.C;
+  out->res_buf = o.res.buf; out->res_c0 = o.res.coff; out->res_c = o.res.C;
+  const OpPlan* pl[2] = {&h->plan_fwd[idx], &h->plan_bwd[idx]};
+  for (int k = 0; k < 2; ++k) {
+    out->nwait[k] = pl[k]->nwait; out->record[k] = pl[k]->record;
+    for (int i = 0; i < pl[k]->nwait && i < 3; ++i) out->wait_op[k][i] = pl[k]->wait_op[i];
+  }
+  return DR_OK;
+}
+
 int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
 int64_t dr_tc_launch_count(const dr_handle* h) { return h ? h->tc_launches : 0; }
 size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes : 0; }

@@ -203,6 +203,21 @@ DR_API int dr_trace(dr_handle* h, int on);
 DR_API int dr_trace_count(const dr_handle* h);
 DR_API int dr_trace_get(const dr_handle* h, int idx, dr_trace_rec* out);
 
+/* One op of the execution graph with its lane plan (debug / tests; works without a GPU).  The library runs independent branches of
+ * um_v1 -- the `upper1` block of every hourglass level (network/um_v1.py:54-65), the masked um branch (:143-149), projection skips
+ * (:31-47) -- on separate CUDA streams ("lanes"); a build-time hazard analysis over the buffer views each op reads / writes decides
+ * which events an op waits for.  tests/test_oracle_net.py re-derives every hazard by brute force from this table. */
+typedef struct {
+  int32_t kind;             /* 0 conv, 1 max-pool, 2 upsample+add, 3 masked copy */
+  int32_t lane, layer, need_dgrad, raw_buf;
+  int32_t in_buf, in_c0, in_c;      /* views: buffer id, first channel, channels */
+  int32_t out_buf, out_c0, out_c;
+  int32_t res_buf, res_c0, res_c;   /* residual operand (conv) / low-resolution operand (upsample+add); buf < 0: none */
+  int32_t nwait[2], wait_op[2][3], record[2];   /* [0] forward pass, [1] backward pass: ops (of other lanes) whose event this op waits for */
+} dr_op_info;
+DR_API int dr_num_ops(const dr_handle* h);
+DR_API int dr_debug_op(const dr_handle* h, int idx, dr_op_info* out);
+
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 DR_API int64_t dr_launch_count(const dr_handle* h);
 /* how many of those were tcgen05 (tensor-core) conv kernels */

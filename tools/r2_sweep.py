@@ -5,14 +5,10 @@ Each child checks the training micro-step against the fp32 FFMA engine (GPU vs G
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
-CONFIGS = [   # round-2 third pass: lanes (multi-stream op scheduling) on top of the adopted defaults
+CONFIGS = [   # round-2 fourth pass: two wgrad side streams, SIMT wgrad splits for tiny maps
     ("base", {}),
+    ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
-    ("no_lanes_no_side", {"DENSEREG_LANES": "0", "DENSEREG_SIDE_STREAM": "0"}),
-    ("lanes_no_side", {"DENSEREG_SIDE_STREAM": "0"}),
-    ("wgrad_w2", {"DENSEREG_WGRAD_WAVES": "2"}),
-    ("wgrad_a_tmem", {"DENSEREG_WGRAD_A_TMEM": "1"}),
-    ("a_tmem_0", {"DENSEREG_TC_A_TMEM": "0"}),
     ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
 ]
 want = set(sys.argv[1:])
