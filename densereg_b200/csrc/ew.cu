@@ -456,12 +456,15 @@ __global__ void bias_bwd_kernel(size_t npix, int C, const float* __restrict__ dy
   }
 }
 
-// GT synthesis + 3 l2 losses + dL/d(out) for every stack; one thread per (b, pixel), loop over joints.
+// GT synthesis + 3 l2 losses + dL/d(out) for every stack; one thread per (b, pixel, joint): consecutive threads take consecutive joints of
+// one pixel, so the hm / hm3 rows (J floats) and the um row (3J floats) are read and written contiguously.  (The first version looped over
+// the joints inside one thread per pixel: 40960 threads for batch 40, 101 us for 52 MB of traffic.)
 __global__ void loss_kernel(LossArgs a) {
   const int hw = a.hw, J = a.J;
-  const size_t n = (size_t)a.B * hw * hw;
+  const size_t n = (size_t)a.B * hw * hw * J;
   double l_hm = 0.0, l_hm3 = 0.0, l_um = 0.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / J; const int j = (int)(t - i * J);
     int b = (int)(i / (hw * hw)); int r = (int)(i - (size_t)b * hw * hw);
     int py = r / hw, px = r - py * hw;
     const float* cfg = a.cfgs + b * 6; const float* com = a.coms + b * 3;
@@ -471,7 +474,7 @@ __global__ void loss_kernel(LossArgs a) {
     float z = d < -0.99f ? com[2] + 150.0f : d * 300.0f + (com[2] - 150.0f);
     float X = ((float)px - cx) * (z / fx), Y = ((float)py - cy) * (z / fy);
     float Pn0 = (X - com[0]) / 100.0f, Pn1 = (Y - com[1]) / 100.0f, Pn2 = (z - com[2]) / 100.0f;
-    for (int j = 0; j < J; ++j) {
+    {
       const float* pose = a.poses + (size_t)b * 3 * J + 3 * j;
       float o0 = (pose[0] - com[0]) / 100.0f - Pn0;
       float o1 = (pose[1] - com[1]) / 100.0f - Pn1;
@@ -706,8 +709,8 @@ int launch_bias_bwd(size_t npix, int C, const float* dy, int dy_cs, const float*
   return 1;
 }
 int launch_loss(const LossArgs& a, cudaStream_t st) {
-  size_t n = (size_t)a.B * a.hw * a.hw;
-  loss_kernel<<<blocks_for(n, EW_T, 148 * 8), EW_T, 0, st>>>(a);
+  size_t n = (size_t)a.B * a.hw * a.hw * a.J;
+  loss_kernel<<<blocks_for(n, EW_T * 2, 148 * 8), EW_T, 0, st>>>(a);
   return 1;
 }
 int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, double* reg_acc, cudaStream_t st) {

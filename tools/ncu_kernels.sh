@@ -36,4 +36,16 @@ cap step_prep_weights      prep_weights_kernel   0 1 $STEP
 cap step_stem_conv         conv_fwd_kernel       1 1 $STEP
 cap infer_vote             vote_kernel           1 1 python tools/step_once.py --infer --micro 2 --batch 64
 cap vote_microbench        vote_kernel           2 1 python tools/bench_vote.py --batch 1024 --iters 2 --cpu_samples 0
-ls -la gpurun_out/ncu | head -60
+# the reports are ~4 MB each and gpurun brings back at most 64 MiB: summarise them here, keep the raw metric tables (gzip) and three reports
+python tools/ncu_summary.py gpurun_out/ncu > gpurun_out/r2_kernels.md 2> gpurun_out/ncu/summary.err
+for f in gpurun_out/ncu/*.ncu-rep; do
+  b=$(basename $f .ncu-rep)
+  ncu -i $f --page raw --csv 2>/dev/null | gzip -9 > gpurun_out/ncu/$b.raw.csv.gz
+done
+for b in wgrad_um_comb_c2 conv_atmem_um_res1_c2 step_wgrad; do
+  ncu -i gpurun_out/ncu/$b.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/ncu/$b.source.csv.gz
+done
+mkdir -p gpurun_out/ncu_keep
+mv gpurun_out/ncu/conv_pair_um_comb_c2.ncu-rep gpurun_out/ncu/conv_atmem_um_res1_c2.ncu-rep gpurun_out/ncu/wgrad_um_comb_c2.ncu-rep gpurun_out/ncu_keep/ 2>/dev/null
+rm -f gpurun_out/ncu/*.ncu-rep
+du -sh gpurun_out/ncu gpurun_out/ncu_keep; cat gpurun_out/r2_kernels.md
