@@ -15,8 +15,9 @@
 //   Both K-major, SWIZZLE_128B (32 fp32 = 128 B rows, 8-row 1024 B atoms): UMMA smem descriptors advance
 //   32 B per K=8 MMA.  DR_PREC_TF32X3: four splitter warps rewrite each landed A tile in shared memory into
 //   hi = rn_tf32(v) and lo = rn_tf32(v - hi), the weights arrive pre-split (two TMA boxes), and every k-step issues hi*lo + lo*hi + hi*hi into the same TMEM accumulator (fp32-class accuracy; algorithmic FLOPs unchanged).
-// Warp roles (192 / 320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
-//   (TMEM lane quarter = warp_idx % 4), warps 6-9 operand splitter (3xTF32 only).  mbarrier full/empty ring.
+// Warp roles (384 threads = 3 warpgroups, registers moved to the epilogue warpgroup with setmaxnreg): warp 0 TMA producer, warp 1 TMEM alloc +
+//   MMA issuer, warps 2-3 idle, warps 4-7 operand splitter (3xTF32 only), warps 8-11 epilogue (TMEM lane quarter = warp_idx % 4).
+//   mbarrier full/empty ring.
 #include "conv_tc_epilogue.cuh"
 #include <stdlib.h>
 
@@ -30,7 +31,7 @@ using namespace tc;
 // L2); the smem ring runs continuously across tiles and the accumulator is double-buffered in TMEM (2 x BN columns), so the
 // epilogue of tile i (TMEM -> registers -> global, BRN statistics) overlaps the main loop of tile i+1.
 template <bool SPLIT3>
-__global__ void __launch_bounds__(SPLIT3 ? 192 + SPLIT_THREADS : 192, 1)
+__global__ void __launch_bounds__(TC1_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -50,11 +51,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // Two-level accumulation (p.chunk_kb > 0): the tensor core's fp32 accumulate truncates, which biases long reductions (measured 1.6e-5 of
   // the output scale at K = 2304 against 3e-7 for FFMA).  The k-blocks of a tile are therefore cut into chunks of `ch`; each chunk is summed
   // by the MMAs into one of the two partial accumulator stages (first MMA of the chunk overwrites), and the epilogue warps add finished
-  // partials into a running sum held in tensor memory (columns 2*BN ...) with round-to-nearest fp32 adds while the MMAs fill the other
-  // stage.  The last partial is combined with the running sum on the fly by tc_epilogue_tile.  Tiles with num_kb <= ch are unchanged.
+  // partials into a running sum held in their registers with round-to-nearest fp32 adds while the MMAs fill the other stage
+  // (conv_tc_epilogue.cuh: tc_flush_partial / tc_fold_running).  Tiles with num_kb <= ch are unchanged.
   const int ch = (p.chunk_kb > 0 && num_kb > p.chunk_kb) ? p.chunk_kb : num_kb;
   const int nchunks = (num_kb + ch - 1) / ch;
-  const uint32_t run_col = 2u * (uint32_t)p.BN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], SPLIT_THREADS / 32); }
@@ -70,6 +70,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < TC1_WARP_SPLIT0) {
+  DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -135,7 +137,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp < 6) {
+  }
+  } else if (warp >= TC1_WARP_EPI0) {
+    DR_SETMAXNREG_INC(REG_EPI);                           // warpgroup 2 (epilogue)
     // ===================== epilogue: TMEM -> registers -> global =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
     __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
@@ -143,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ int s_last;
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int et = q * 32 + lane;                        // 0..127 (warps 2..5 -> q = 2,3,0,1)
+    const int et = q * 32 + lane;                        // 0..127
     const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     tc_epilogue_stage_affine(p, et, s_scale, s_shift);
@@ -151,38 +155,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
-      for (int c = 0; c < nchunks; ++c, ++ccount) {
+      float run[4][32];                                   // running sum of this tile's finished partials (two-level accumulation only)
+      for (int c = 0; c + 1 < nchunks; ++c, ++ccount) {
+        const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+        mbar_wait_sleep(&acc_full[as], aph);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + as * (uint32_t)p.BN + lane_bits;
+        if (c == 0) tc_flush_partial<true>(tl, p.BN, run); else tc_flush_partial<false>(tl, p.BN, run);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);       // the MMA warp may overwrite this partial stage
+      }
+      {
         const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
         mbar_wait_sleep(&acc_full[as], aph);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * (uint32_t)p.BN;
-        if (c + 1 < nchunks) {
-          // flush: running (+)= partial, this warp's 32 lanes, round-to-nearest fp32 adds; then hand the stage back to the MMA warp
-          for (int cb = 0; cb < p.BN; cb += 32) {
-            uint32_t v[32];
-            tmem_ld32(tacc + lane_bits + (uint32_t)cb, v);
-            if (c > 0) {
-              uint32_t r2[32];
-              tmem_ld32(tmem_base + lane_bits + run_col + (uint32_t)cb, r2);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(r2[i]), __uint_as_float(v[i])));
-            }
-            tmem_st32(tmem_base + lane_bits + run_col + (uint32_t)cb, v);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
-        } else {
-          tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
-                           s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); }, tmem_base + run_col, nchunks > 1);
-        }
+        if (nchunks > 1) tc_fold_running(tacc + lane_bits, p.BN, run);
+        tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
+                         s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
+        ++ccount;
       }
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
-  } else if (SPLIT3) {
+  } else {
+    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroup 1 (splitters; idle for single-pass tf32)
+    if (SPLIT3) {
     // ===================== A splitter: hi = rn_tf32(a), lo = rn_tf32(a - hi) =====================
-    const int t = threadIdx.x - 192;                      // 0..SPLIT_THREADS-1
+    const int t = threadIdx.x - TC1_WARP_SPLIT0 * 32;     // 0..SPLIT_THREADS-1
     const int na4 = A_TILE_BYTES / 16;                    // weights arrive pre-split (hi, lo) by TMA; only the A tile is split here
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -205,6 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);                       // one arrival per splitter warp
       }
+    }
     }
   }
 
@@ -244,13 +245,13 @@ bool conv_tc_eligible(const ConvProblem& p) {
 int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
   // two-level accumulation (kernel comment): ConvProblem::chunk_kb = k-blocks per partial accumulator, 0 = off (the engine sets it: on for
-  // inference, off for training -- engine.cu).  3xTF32 only; chunked layers run on this kernel (the CTA-pair kernel's tensor memory is full
-  // with two 256-column accumulator stages).
+  // inference, off for training -- engine.cu).  3xTF32 only; chunked layers run on this kernel or on the A-in-tensor-memory kernel (a 256-column
+  // tile of the CTA-pair kernel would need 256 registers per epilogue thread for its running sum).
   const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : 0;
   const int num_kb_all = p.k * p.k * ((p.Cin + TC_BK - 1) / TC_BK);
   const bool chunked = split3 && chunk_kb > 0 && num_kb_all > chunk_kb && num_kb_all > p.chunk_min_kb;   // short reductions stay one-level
-  if (split3 && !chunked) {
-    const bool pair_w = conv_tc_pair_wanted(p);
+  if (split3) {
+    const bool pair_w = !chunked && conv_tc_pair_wanted(p);   // the CTA-pair kernel (BN = 256) has no register room for a running sum
     const int am = conv_tc_atmem_mode();                   // opt-in: split A operand in tensor memory (conv_tc_atmem.cu)
     if (am == 2 || (am == 1 && !pair_w)) {
       const int n = launch_conv_tc_atmem(p, st);
@@ -267,7 +268,7 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
     if (bn_cap >= 16 && BN > bn_cap) BN = bn_cap / 16 * 16; }
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
-  int cols = 32; while (cols < (chunked ? 2 * BN + (BN + 31) / 32 * 32 : 2 * BN)) cols <<= 1;   // two accumulator stages (+ the running sum)
+  int cols = 32; while (cols < 2 * BN) cols <<= 1;         // two accumulator stages
   t.tmem_cols = cols;
   t.chunk_kb = chunked ? chunk_kb : 0;
   t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;
@@ -317,11 +318,11 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (split3) {
     if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[1] = true; }
-    conv_tc_kernel<true><<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+    conv_tc_kernel<true><<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
     return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<3xTF32>") ? 1 : 0;
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[0] = true; }
-    conv_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(ma, mw, mwlo, t);
+    conv_tc_kernel<false><<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   }
   return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<TF32>") ? 1 : 0;
 }

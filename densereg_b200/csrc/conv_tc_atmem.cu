@@ -45,7 +45,7 @@ DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, 
 }
 
 // dynamic smem (1024 B aligned): [stage][A fp32 16K | B hi BN*128 | B lo BN*128] ... barriers ... tmem ptr
-__global__ void __launch_bounds__(192 + SPLIT_THREADS, 1)
+__global__ void __launch_bounds__(TC1_THREADS, 1)
 conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -63,6 +63,9 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const uint32_t a_col0 = (2u * (uint32_t)p.BN + 31u) & ~31u;      // first tensor-memory column of the A ring (32-column aligned)
+  // two-level accumulation (see conv_tc.cu): chunks of `ch` k-blocks per partial accumulator stage, running sum in the epilogue warps' registers
+  const int ch = (p.chunk_kb > 0 && num_kb > p.chunk_kb) ? p.chunk_kb : num_kb;
+  const int nchunks = (num_kb + ch - 1) / ch;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], SPLIT_THREADS / 32); }
@@ -78,6 +81,8 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < TC1_WARP_SPLIT0) {
+  DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -108,32 +113,37 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&split_bar[s], ph);                // A hi / lo of this stage are in tensor memory, B hi / lo in shared memory
+      uint32_t it = 0, ccount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++ccount) {
+          const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+          mbar_wait(&acc_empty[as], aph ^ 1);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + A_TILE_BYTES;
-          const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+          const int kb0 = c * ch, kb1 = kb0 + ch < num_kb ? kb0 + ch : num_kb;
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&split_bar[s], ph);                // A hi / lo of this stage are in tensor memory, B hi / lo in shared memory
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + A_TILE_BYTES;
+            const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t bd = make_desc(b_addr + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
-            tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bld, idesc, (kb | k) != 0);     // hi * lo
-            tc_mma_tf32_ts(tmem_d, a_lo + 8u * k, bd, idesc, 1);                  // lo * hi
-            tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bd, idesc, 1);                  // hi * hi
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t bd = make_desc(b_addr + k * 32), bld = make_desc(b_addr + b_bytes + k * 32);
+              tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bld, idesc, ((kb - kb0) | k) != 0);   // hi * lo (first MMA of a chunk overwrites)
+              tc_mma_tf32_ts(tmem_d, a_lo + 8u * k, bd, idesc, 1);                          // lo * hi
+              tc_mma_tf32_ts(tmem_d, a_hi + 8u * k, bd, idesc, 1);                          // hi * hi
+            }
+            tc_commit(&empty_bar[s]);
           }
-          tc_commit(&empty_bar[s]);
+          tc_commit(&acc_full[as]);
         }
-        tc_commit(&acc_full[as]);
       }
     }
-  } else if (warp < 6) {
+  }
+  } else if (warp >= TC1_WARP_EPI0) {
+    DR_SETMAXNREG_INC(REG_EPI);                           // warpgroup 2 (epilogue)
     // ===================== epilogue (shared with conv_tc.cu) =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
     __shared__ __align__(16) float s_scale[TC_MAX_COUT], s_shift[TC_MAX_COUT];
@@ -145,19 +155,37 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const bool vec_ok = ((p.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || (((p.res_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     tc_epilogue_stage_affine(p, et, s_scale, s_shift);
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t ccount = 0;
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tile_m = tile / p.tiles_n, n0 = (tile - tile_m * p.tiles_n) * p.BN;
-      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-      mbar_wait_sleep(&acc_full[as], aph);
-      tc_fence_after();
-      tc_epilogue_tile(p, tmem_base + as * (uint32_t)p.BN, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
-                       s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
+      float run[4][32];                                   // running sum of this tile's finished partials (two-level accumulation only)
+      for (int c = 0; c + 1 < nchunks; ++c, ++ccount) {
+        const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+        mbar_wait_sleep(&acc_full[as], aph);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + as * (uint32_t)p.BN + lane_bits;
+        if (c == 0) tc_flush_partial<true>(tl, p.BN, run); else tc_flush_partial<false>(tl, p.BN, run);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);       // the MMA warp may overwrite this partial stage
+      }
+      {
+        const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
+        mbar_wait_sleep(&acc_full[as], aph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.BN;
+        if (nchunks > 1) tc_fold_running(tacc + lane_bits, p.BN, run);
+        tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
+                         s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
+        ++ccount;
+      }
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
   } else {
+    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroup 1 (splitters)
     // ===================== A splitter: shared memory (fp32, 128B-swizzled rows) -> registers -> tensor memory (hi | lo) =====================
-    // warps 6..9: warp % 4 = 2, 3, 0, 1 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
+    // warps 4..7: warp % 4 = 0..3 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
     const int q = warp & 3;
     const int r = q * 32 + lane;                          // pixel row of the tile == tensor-memory lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
@@ -231,6 +259,8 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
   if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
   t.stages = stages;
+  { const int nk = p.k * p.k * t.kblocks_per_tap;
+    t.chunk_kb = (p.chunk_kb > 0 && nk > p.chunk_kb && nk > p.chunk_min_kb) ? p.chunk_kb : 0; }
   int cols = 32; while (cols < a_col0 + 64 * stages) cols <<= 1;
   t.tmem_cols = cols;
   t.y = p.y; t.y_cs = p.y_cs; t.scale = p.scale; t.shift = p.shift; t.relu = p.relu; t.res = p.res; t.res_cs = p.res_cs;
@@ -264,6 +294,6 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
     if (cudaFuncSetAttribute(conv_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
   }
-  conv_tc_atmem_kernel<<<grid, 192 + SPLIT_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+  conv_tc_atmem_kernel<<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   return 1;
 }

@@ -10,6 +10,15 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // fp32 elements per k-block = one 128 B swizzle row
 constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4; // 16 KB
 constexpr int SPLIT_THREADS = 128;             // 4 splitter warps (3xTF32); 8 measured slower (issue-slot pressure on the MMA thread)
+// One-CTA kernels (conv_tc.cu, conv_tc_atmem.cu): three warpgroups so that registers can be moved between roles with setmaxnreg --
+//   warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer (+ tensor-memory alloc), warps 2-3 idle;  warpgroup 1: operand splitters;
+//   warpgroup 2: epilogue.  A 384-thread CTA gets 168 registers per thread at launch; the control and splitter warpgroups hand most of theirs
+//   to the epilogue warps, which then have room for the running sums of the two-level accumulation (128 registers for a 128-column tile).
+constexpr int TC1_THREADS = 384;
+constexpr int TC1_WARP_SPLIT0 = 4, TC1_WARP_EPI0 = 8;
+constexpr int REG_CTRL = 40, REG_SPLIT = 96, REG_EPI = 232;
+#define DR_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
+#define DR_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
 
 struct TcParams {
   int M;                 // B*H*W output pixels
@@ -62,12 +71,10 @@ DR_DEVINL void tc_epilogue_stage_affine(const TcParams& p, int et, float* s_scal
 // 32-column chunk, and the residual / accumulate operands of a chunk are fetched as one batch of independent 16 B loads, so the chunk
 // is a straight line of independent instructions (the first version interleaved two dependent global loads and four branches per
 // element: 0.1 instructions per cycle per warp, 12 us per 128x128 tile -- profiles/r1_epilogue.md).
-// tmem_acc2 / has2: a second accumulator (same lanes / column layout) whose values are ADDED (fp32, round to nearest) to the first one before
-// anything else -- the running sum of the earlier K chunks in the two-level accumulation mode.
 template <class Release>
 DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int lane, int row, int et, bool vec_ok, int tile_m, int n0, int bn,
                                 int total_tiles, float (*s_sum)[256], float (*s_sq)[256], int& s_last, float* s_scale,
-                                float* s_shift, float* stg, Release release, uint32_t tmem_acc2 = 0, bool has2 = false) {
+                                float* s_shift, float* stg, Release release) {
     const int m = tile_m * TC_BM + row;
     const bool mvalid = m < p.M;
     float* yr = p.y + (size_t)m * p.y_cs;
@@ -76,12 +83,6 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
     for (int cb = 0; cb < bn; cb += 32) {          // bn = columns of this work item (p.BN)
       uint32_t v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-      if (has2) {
-        uint32_t r2[32];
-        tmem_ld32(tmem_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r2);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(r2[i]), __uint_as_float(v[i])));
-      }
       if (p.stats) {
         // column sums over this warp's 32 rows by recursive halving: 31 shuffles, lane l ends with column cb+l
         float a[32], b2[32];
@@ -239,6 +240,37 @@ DR_DEVINL void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, int q, int
         brn_finalize_dev<1, 128>(et, p.Cout, (double)p.M, p.stats, p.bn_bg, p.bn_state, p.bn_aff, p.bn_bstat, p.bn_update_state);
       }
     }
+}
+
+// ---- two-level accumulation (TcParams::chunk_kb): running sums of the finished partial accumulators live in REGISTERS of the epilogue
+// warps -- lane = accumulator row, run[j][i] = column 32*j + i (BN <= 128) -- so a flush is one tensor-memory read of the partial (~1000
+// cycles for 128 x 128 at 64 B/clk, hidden behind the >= 1300 MMA cycles of the next k-block) and round-to-nearest fp32 adds.
+template <bool FIRST>
+DR_DEVINL void tc_flush_partial(uint32_t tacc_lane, int bn, float (&run)[4][32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j * 32 < bn) {
+      uint32_t v[32];
+      tmem_ld32(tacc_lane + (uint32_t)(j * 32), v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) run[j][i] = FIRST ? __uint_as_float(v[i]) : __fadd_rn(run[j][i], __uint_as_float(v[i]));
+    }
+  }
+}
+// last chunk of a tile: partial += running sum, written back into the partial's own tensor-memory columns so that the (unchanged) epilogue
+// reads the complete accumulator from there
+DR_DEVINL void tc_fold_running(uint32_t tacc_lane, int bn, const float (&run)[4][32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j * 32 < bn) {
+      uint32_t v[32];
+      tmem_ld32(tacc_lane + (uint32_t)(j * 32), v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(run[j][i], __uint_as_float(v[i])));
+      tmem_st32(tacc_lane + (uint32_t)(j * 32), v);
+    }
+  }
+  tmem_wait_st();
 }
 
 // After a CTA's last tile (per-CTA statistics mode only): publish the running totals with one round of double atomics, then the usual
