@@ -109,7 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
           mbar_wait(&acc_empty[as], aph ^ 1);            // epilogue has drained this accumulator stage
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.acc_stride;
           const int kb0 = c * ch, kb1 = kb0 + ch < num_kb ? kb0 + ch : num_kb;
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % p.stages;
@@ -160,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
         mbar_wait_sleep(&acc_full[as], aph);
         tc_fence_after();
-        const uint32_t tl = tmem_base + as * (uint32_t)p.BN + lane_bits;
+        const uint32_t tl = tmem_base + as * (uint32_t)p.acc_stride + lane_bits;
         if (c == 0) tc_flush_partial<true>(tl, p.BN, run); else tc_flush_partial<false>(tl, p.BN, run);
         tc_fence_before();
         __syncwarp();
@@ -170,7 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
         mbar_wait_sleep(&acc_full[as], aph);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * (uint32_t)p.BN;
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
         if (nchunks > 1) tc_fold_running(tacc + lane_bits, p.BN, run);
         tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
                          s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
@@ -268,7 +268,8 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
     if (bn_cap >= 16 && BN > bn_cap) BN = bn_cap / 16 * 16; }
   t.BN = BN;
   t.kblocks_per_tap = (p.Cin + TC_BK - 1) / TC_BK;
-  int cols = 32; while (cols < 2 * BN) cols <<= 1;         // two accumulator stages
+  t.acc_stride = (BN + 31) / 32 * 32;
+  int cols = 32; while (cols < 2 * t.acc_stride) cols <<= 1;   // two accumulator stages
   t.tmem_cols = cols;
   t.chunk_kb = chunked ? chunk_kb : 0;
   t.tiles_m = (t.M + TC_BM - 1) / TC_BM; t.tiles_n = (p.Cout + BN - 1) / BN;

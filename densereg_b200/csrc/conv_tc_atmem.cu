@@ -45,7 +45,7 @@ DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, 
 }
 
 // dynamic smem (1024 B aligned): [stage][A fp32 16K | B hi BN*128 | B lo BN*128] ... barriers ... tmem ptr
-__global__ void __launch_bounds__(TC1_THREADS, 1)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -60,9 +60,10 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int epi_warp0 = p.split_groups > 1 ? TC2_WARP_EPI0 : TC1_WARP_EPI0;     // 512 threads with two splitter warpgroups, 384 with one
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  const uint32_t a_col0 = (2u * (uint32_t)p.BN + 31u) & ~31u;      // first tensor-memory column of the A ring (32-column aligned)
+  const uint32_t a_col0 = 2u * (uint32_t)p.acc_stride;             // first tensor-memory column of the A ring (behind the two accumulator stages)
   // two-level accumulation (see conv_tc.cu): chunks of `ch` k-blocks per partial accumulator stage, running sum in the epilogue warps' registers
   const int ch = (p.chunk_kb > 0 && num_kb > p.chunk_kb) ? p.chunk_kb : num_kb;
   const int nchunks = (num_kb + ch - 1) / ch;
@@ -81,7 +82,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < TC1_WARP_SPLIT0) {
+  if (warp < TC2_WARP_SPLIT0) {
   DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -119,7 +120,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
           mbar_wait(&acc_empty[as], aph ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.BN;
+          const uint32_t tmem_d = tmem_base + as * (uint32_t)p.acc_stride;
           const int kb0 = c * ch, kb1 = kb0 + ch < num_kb ? kb0 + ch : num_kb;
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % p.stages;
@@ -142,7 +143,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   }
-  } else if (warp >= TC1_WARP_EPI0) {
+  } else if (warp >= epi_warp0) {
     DR_SETMAXNREG_INC(REG_EPI);                           // warpgroup 2 (epilogue)
     // ===================== epilogue (shared with conv_tc.cu) =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
@@ -164,7 +165,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
         mbar_wait_sleep(&acc_full[as], aph);
         tc_fence_after();
-        const uint32_t tl = tmem_base + as * (uint32_t)p.BN + lane_bits;
+        const uint32_t tl = tmem_base + as * (uint32_t)p.acc_stride + lane_bits;
         if (c == 0) tc_flush_partial<true>(tl, p.BN, run); else tc_flush_partial<false>(tl, p.BN, run);
         tc_fence_before();
         __syncwarp();
@@ -174,7 +175,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t as = ccount & 1, aph = (ccount >> 1) & 1;
         mbar_wait_sleep(&acc_full[as], aph);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * (uint32_t)p.BN;
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
         if (nchunks > 1) tc_fold_running(tacc + lane_bits, p.BN, run);
         tc_epilogue_tile(p, tacc, q, lane, row, et, vec_ok, tile_m, n0, p.BN, total_tiles, s_sum, s_sq, s_last,
                          s_scale, s_shift, s_stage[q], [&]() { mbar_arrive(&acc_empty[as]); });
@@ -183,15 +184,17 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
   } else {
-    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroup 1 (splitters)
+    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroups 1 and 2 (splitters: even / odd ring iterations)
+    const uint32_t sgrp = warp >= TC2_WARP_SPLIT1 ? 1u : 0u, sgroups = (uint32_t)p.split_groups;
     // ===================== A splitter: shared memory (fp32, 128B-swizzled rows) -> registers -> tensor memory (hi | lo) =====================
-    // warps 4..7: warp % 4 = 0..3 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
+    // warps 4..7 / 8..11: warp % 4 = 0..3 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
     const int q = warp & 3;
     const int r = q * 32 + lane;                          // pixel row of the tile == tensor-memory lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        if (sgroups > 1 && (it & 1u) != sgrp) continue;   // the other splitter warpgroup takes this k-block
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -251,14 +254,16 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
     smem_budget = 227 * 1024 - (int)st_bytes - 1536;
   }
   int stages = smem_budget / stage_bytes;
-  const int a_col0 = (2 * BN + 31) / 32 * 32;
+  const int acc_stride = (BN + 31) / 32 * 32;
+  const int a_col0 = 2 * acc_stride;
   const int tmem_stages = (512 - a_col0) / 64;
   if (stages > tmem_stages) stages = tmem_stages;
   if (stages > 6) stages = 6;
   if (stages < 2) return 0;
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
   if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
-  t.stages = stages;
+  t.stages = stages; t.acc_stride = acc_stride;
+  { static int sg = -1; if (sg < 0) { const char* e = getenv("DENSEREG_TC_SPLIT_GROUPS"); sg = (e && e[0] == '1') ? 1 : 2; } t.split_groups = sg; }
   { const int nk = p.k * p.k * t.kblocks_per_tap;
     t.chunk_kb = (p.chunk_kb > 0 && nk > p.chunk_kb && nk > p.chunk_min_kb) ? p.chunk_kb : 0; }
   int cols = 32; while (cols < a_col0 + 64 * stages) cols <<= 1;
@@ -294,6 +299,6 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
     if (cudaFuncSetAttribute(conv_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
   }
-  conv_tc_atmem_kernel<<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+  conv_tc_atmem_kernel<<<grid, t.split_groups > 1 ? TC2_THREADS : TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   return 1;
 }

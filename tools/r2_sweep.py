@@ -5,11 +5,14 @@ Each child checks the training micro-step against the fp32 FFMA engine (GPU vs G
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
-CONFIGS = [   # round-2 fourth pass: two wgrad side streams, SIMT wgrad splits for tiny maps
+CONFIGS = [   # round-2 fifth pass: setmaxnreg role layout, register-resident running sums, two splitter warpgroups in the A-TMEM conv kernel
     ("base", {}),
+    ("split_groups_1", {"DENSEREG_TC_SPLIT_GROUPS": "1"}),
+    ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
+    ("a_tmem_0", {"DENSEREG_TC_A_TMEM": "0"}),
+    ("chunk_train_1", {"DENSEREG_TC_CHUNK_TRAIN": "1"}),
     ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
-    ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
 ]
 want = set(sys.argv[1:])
 path = os.path.join(OUT, "r2_sweep.jsonl")
