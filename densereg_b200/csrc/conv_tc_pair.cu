@@ -238,7 +238,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 bool conv_tc_pair_wanted(const ConvProblem& p) {
   if (!p.pair || !p.w_kmajor_lo) return false;
   if (p.pair >= 2) return p.Cout >= 16;                    // forced (dr_debug_conv flag 0x200): any shape the pair kernel can run
-  if (p.Cout < 128) return false;
+  static int min_cout = -1;       // DENSEREG_TC_PAIR_MINCOUT: narrowest layer that takes the pair kernel (default 128)
+  if (min_cout < 0) { const char* e = getenv("DENSEREG_TC_PAIR_MINCOUT"); min_cout = e ? atoi(e) : 128; if (min_cout < 32) min_cout = 32; }
+  if (p.Cout < min_cout) return false;
   const int M = p.B * p.H * p.W;
   int BN = (p.Cout + 15) / 16 * 16; if (BN > 256) BN = 256;
   const int items = ((M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((p.Cout + BN - 1) / BN);

@@ -95,8 +95,8 @@ struct dr_handle {
   // two-level accumulation of the 3xTF32 convs (conv_tc.cu): k-blocks per partial accumulator.  Inference (the path whose joint positions
   // are compared with the reference in mm) sums ONE k-block = 32 input channels (12 MMAs) inside the tensor core; training keeps one level
   // (its gradients sit on the fp32 noise floor of the graph either way, and the CTA-pair kernel has no room for a running sum).
-  // DENSEREG_TC_CHUNK overrides both, DENSEREG_TC_CHUNK_EVAL / DENSEREG_TC_CHUNK_TRAIN one of them.
-  int chunk_eval = 1, chunk_train = 0, chunk_min_kb = 0;
+  // DENSEREG_TC_CHUNK_EVAL overrides the inference setting (0 = one level, "throughput mode").
+  int chunk_eval = 1, chunk_min_kb = 0;
   // backward: filter gradients run on a side stream (they only feed the optimiser) so that they fill the SMs the small
   // BRN / low-resolution kernels of the main stream leave idle; d(raw) scratch is triple-buffered for that
   static const int kSlotsPerLane = 3;
@@ -734,7 +734,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
         p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
         p.k = L.k; p.stride = L.stride; p.pad_t = p.pad_l = same_pad_before(L.in_hw, L.k, L.stride);
         set_fwd_weights(h, L, h->precision, p);
-        p.chunk_kb = training ? h->chunk_train : h->chunk_eval; p.chunk_min_kb = h->chunk_min_kb;
+        p.chunk_kb = training ? 0 : h->chunk_eval; p.chunk_min_kb = h->chunk_min_kb;      // two-level accumulation: inference only
         const float* aff = h->aff + L.aff_off;
         const float* res = o.res.buf >= 0 ? X.ptr(o.res) : nullptr;
         const int res_cs = o.res.buf >= 0 ? X.cs(o.res) : 0;
@@ -876,7 +876,6 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.Ho = L.in_hw; p.Wo = L.in_hw; p.Cout = L.cin; p.k = L.k; p.stride = 1;
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
           set_dgrad_weights(h, L, h->precision, p);
-          p.chunk_kb = h->chunk_train; p.chunk_min_kb = h->chunk_min_kb;
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
           RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
@@ -1066,9 +1065,7 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   { const char* env = getenv("DENSEREG_TC_PAIR"); h->tc_pair = cfg->reserved[1] >= 0 && !(env && env[0] == '0'); }
   { const char* env = getenv("DENSEREG_PREP_ONCE"); h->prep_once = !(env && env[0] == '0'); }
   { const char* env = getenv("DENSEREG_LANES"); h->lanes_on = !(env && env[0] == '0'); }
-  { const char* e = getenv("DENSEREG_TC_CHUNK"); if (e) { h->chunk_eval = h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; } }
   { const char* e = getenv("DENSEREG_TC_CHUNK_EVAL"); if (e) h->chunk_eval = atoi(e) > 0 ? atoi(e) : 0; }
-  { const char* e = getenv("DENSEREG_TC_CHUNK_TRAIN"); if (e) h->chunk_train = atoi(e) > 0 ? atoi(e) : 0; }
   { const char* e = getenv("DENSEREG_TC_CHUNK_MINKB"); if (e) h->chunk_min_kb = atoi(e) > 0 ? atoi(e) : 0; }
   Builder b{h, 0, 0, 0};
   b.build();

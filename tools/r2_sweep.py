@@ -10,7 +10,9 @@ CONFIGS = [   # round-2 fifth pass: setmaxnreg role layout, register-resident ru
     ("split_groups_1", {"DENSEREG_TC_SPLIT_GROUPS": "1"}),
     ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
     ("a_tmem_0", {"DENSEREG_TC_A_TMEM": "0"}),
-    ("chunk_train_1", {"DENSEREG_TC_CHUNK_TRAIN": "1"}),
+    ("pair_mincout_64", {"DENSEREG_TC_PAIR_MINCOUT": "64"}),
+    ("pair_mincout_80", {"DENSEREG_TC_PAIR_MINCOUT": "80"}),
+    ("pair_mincout_64_w", {"DENSEREG_TC_PAIR_MINCOUT": "64", "DENSEREG_TC_PAIR_MINWORK": "0"}),
     ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
 ]
