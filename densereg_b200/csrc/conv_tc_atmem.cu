@@ -45,7 +45,7 @@ DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, 
 }
 
 // dynamic smem (1024 B aligned): [stage][A fp32 16K | B hi BN*128 | B lo BN*128] ... barriers ... tmem ptr
-__global__ void __launch_bounds__(TC2_THREADS, 1)
+__global__ void __launch_bounds__(TC1_THREADS, 1)
 conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -60,7 +60,6 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int epi_warp0 = p.split_groups > 1 ? TC2_WARP_EPI0 : TC1_WARP_EPI0;     // 512 threads with two splitter warpgroups, 384 with one
   const int num_kb = p.ksz * p.ksz * p.kblocks_per_tap;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const uint32_t a_col0 = 2u * (uint32_t)p.acc_stride;             // first tensor-memory column of the A ring (behind the two accumulator stages)
@@ -82,7 +81,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < TC2_WARP_SPLIT0) {
+  if (warp < TC1_WARP_SPLIT0) {
   DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -143,7 +142,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   }
-  } else if (warp >= epi_warp0) {
+  } else if (warp >= TC1_WARP_EPI0) {
     DR_SETMAXNREG_INC(REG_EPI);                           // warpgroup 2 (epilogue)
     // ===================== epilogue (shared with conv_tc.cu) =====================
     __shared__ float s_sum[4][256], s_sq[4][256];
@@ -184,17 +183,15 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     tc_epilogue_finish(p, et, s_scale, s_shift, s_last);
   } else {
-    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroups 1 and 2 (splitters: even / odd ring iterations)
-    const uint32_t sgrp = warp >= TC2_WARP_SPLIT1 ? 1u : 0u, sgroups = (uint32_t)p.split_groups;
+    DR_SETMAXNREG_DEC(REG_SPLIT);                         // warpgroup 1 (splitters)
     // ===================== A splitter: shared memory (fp32, 128B-swizzled rows) -> registers -> tensor memory (hi | lo) =====================
-    // warps 4..7 / 8..11: warp % 4 = 0..3 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
+    // warps 4..7: warp % 4 = 0..3 -> each owns one 32-lane quarter of tensor memory = 32 pixel rows of the tile
     const int q = warp & 3;
     const int r = q * 32 + lane;                          // pixel row of the tile == tensor-memory lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        if (sgroups > 1 && (it & 1u) != sgrp) continue;   // the other splitter warpgroup takes this k-block
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -263,7 +260,6 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
   const int num_kb = p.k * p.k * t.kblocks_per_tap;
   if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
   t.stages = stages; t.acc_stride = acc_stride;
-  { static int sg = -1; if (sg < 0) { const char* e = getenv("DENSEREG_TC_SPLIT_GROUPS"); sg = (e && e[0] == '1') ? 1 : 2; } t.split_groups = sg; }
   { const int nk = p.k * p.k * t.kblocks_per_tap;
     t.chunk_kb = (p.chunk_kb > 0 && nk > p.chunk_kb && nk > p.chunk_min_kb) ? p.chunk_kb : 0; }
   int cols = 32; while (cols < a_col0 + 64 * stages) cols <<= 1;
@@ -299,6 +295,6 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
     if (cudaFuncSetAttribute(conv_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
   }
-  conv_tc_atmem_kernel<<<grid, t.split_groups > 1 ? TC2_THREADS : TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+  conv_tc_atmem_kernel<<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
   return 1;
 }

@@ -16,12 +16,6 @@ constexpr int SPLIT_THREADS = 128;             // 4 splitter warps (3xTF32); 8 m
 //   to the epilogue warps, which then have room for the running sums of the two-level accumulation (128 registers for a 128-column tile).
 constexpr int TC1_THREADS = 384;
 constexpr int TC1_WARP_SPLIT0 = 4, TC1_WARP_EPI0 = 8;
-// A-in-tensor-memory kernel (conv_tc_atmem.cu): TWO splitter warpgroups that take alternate k-blocks (warps 4-7 even ring iterations, warps 8-11
-// odd ones), epilogue = warps 12-15.  One splitter warp turns a k-block around in ~1400 cycles (8 LDS.128 -> 192 conversions -> 2 tcgen05.st ->
-// wait::st -> fence -> arrive, a latency chain), while the MMAs of a narrow layer (N = 64 / 80) need 400-500: the kernel ran at 35 % tensor activity
-// on um_res1/c2 (profiles/r2_kernels.md) waiting for the split.  Two groups keep two k-blocks in flight.
-constexpr int TC2_THREADS = 512;
-constexpr int TC2_WARP_SPLIT0 = 4, TC2_WARP_SPLIT1 = 8, TC2_WARP_EPI0 = 12;
 constexpr int REG_CTRL = 40, REG_SPLIT = 96, REG_EPI = 232;
 #define DR_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 #define DR_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
@@ -45,7 +39,6 @@ struct TcParams {
   int stats_per_cta;     // fused BRN statistics: accumulate per CTA in shared memory, ONE round of atomics + fence + counter per CTA (opt-in)
   int coalesce;          // epilogue: transpose each 32x32 chunk through shared memory so that global stores / residual loads are whole 128 B rows
   int acc_stride;        // tensor-memory columns per accumulator stage: BN rounded up to 32 (whole tcgen05.ld / st groups belong to ONE stage)
-  int split_groups;      // conv_tc_atmem.cu: 1 or 2 splitter warpgroups (alternate k-blocks)
   int chunk_kb;          // > 0: two-level accumulation -- the tensor core sums at most chunk_kb k-blocks into a partial accumulator (its fp32 adds
                          // truncate), partials are added into a running sum with round-to-nearest fp32 adds by the epilogue warps (conv_tc.cu)
 };

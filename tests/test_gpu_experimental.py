@@ -3,7 +3,6 @@ tests in a child process with the switch set (the switches are read once per pro
 the default suite covers exactly what ships enabled; tools/r2_sweep.py additionally checks every setting against the fp32 engine and times it.
   DENSEREG_WGRAD_A_TMEM=1     persistent wgrad with the split A operand in tensor memory        wgrad_tc.cu
   DENSEREG_TC_A_TMEM=0 | 2    A-in-tensor-memory conv kernel nowhere / also instead of CTA pairs  conv_tc_atmem.cu
-  DENSEREG_TC_SPLIT_GROUPS=1  one splitter warpgroup in the A-in-tensor-memory conv kernel        conv_tc_atmem.cu
   DENSEREG_LANES=0            single stream instead of the lane plan                            engine.cu
   DENSEREG_WGRAD_STREAMS=1, DENSEREG_SIDE_STREAM=0   one / no filter-gradient side stream       engine.cu
   DENSEREG_WGRAD_SWAP=0, DENSEREG_WGRAD_WAVES=2, DENSEREG_BRN_BLOCKS=1184, DENSEREG_TC_STATS_PER_CTA=0, DENSEREG_POOL_BWD_V4=0   the round-1 settings"""
@@ -18,7 +17,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DENSEREG_TEST_
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_A_TMEM": "1"}, {"DENSEREG_TC_A_TMEM": "0"}, {"DENSEREG_TC_A_TMEM": "2"}, {"DENSEREG_TC_SPLIT_GROUPS": "1"},
+@pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_A_TMEM": "1"}, {"DENSEREG_TC_A_TMEM": "0"}, {"DENSEREG_TC_A_TMEM": "2"}, 
                                  {"DENSEREG_LANES": "0"}, {"DENSEREG_WGRAD_STREAMS": "1"}, {"DENSEREG_SIDE_STREAM": "0"},
                                  {"DENSEREG_WGRAD_SWAP": "0", "DENSEREG_WGRAD_WAVES": "2", "DENSEREG_BRN_BLOCKS": "1184", "DENSEREG_TC_STATS_PER_CTA": "0",
                                   "DENSEREG_POOL_BWD_V4": "0"}])
