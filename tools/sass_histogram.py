@@ -4,7 +4,7 @@ instructions.   python tools/sass_histogram.py > profiles/sass_r2.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "densereg_b200", "libdensereg_sm100.so")
-KEY = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UTCCP", "SYNCS", "HMMA", "FFMA",
+KEY = ["USETMAXREG", "UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UTCCP", "SYNCS", "HMMA", "FFMA",
        "LDG", "STG", "RED", "ATOM", "LDS", "STS", "SHFL", "BAR", "MEMBAR", "CCTL", "ERRBAR", "LDL", "STL"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 kern, hist = None, collections.OrderedDict()
@@ -16,7 +16,7 @@ for line in out.splitlines():
     if m and kern:
         op = m.group(1)
         hist[kern][op.split(".")[0]] += 1
-        if op.startswith(("UTC", "UTMA", "LDTM", "STTM")):
+        if op.startswith(("UTC", "UTMA", "LDTM", "STTM", "USETMAXREG")):
             hist[kern]["=" + op] += 1
 dem = subprocess.run(["c++filt"], input="\n".join(hist.keys()), capture_output=True, text=True).stdout.splitlines()
 print("# SASS opcode histogram per kernel of densereg_b200/libdensereg_sm100.so (sm_100a), `cuobjdump -sass`; columns = instruction counts.")
