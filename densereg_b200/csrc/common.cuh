@@ -3,8 +3,34 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
+#include <utility>
 
 #define DR_DEVINL __device__ __forceinline__
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------------------
+// Consecutive kernels of one stream are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may start
+// (launch latency, barrier init, tensor-memory allocation, tensor-map prefetch) while the previous kernel drains, and block in
+// griddepcontrol.wait until it has completed and its memory is visible.  EVERY kernel launched through dr_launch() executes pdl_wait() in all
+// of its threads before it touches global memory; pdl_trigger() lets its own dependents start launching as soon as all of its CTAs are
+// resident.  The step is ~950 launches per micro-batch, most of them 5-20 us on small grids (profiles/r2_final.md).
+#ifdef __CUDACC__
+DR_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DR_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool dr_pdl_enabled();                 // engine.cu: DENSEREG_PDL != 0 and not suspended (CUDA-graph capture)
+void dr_pdl_suspend(int on);
+
+template <class... KArgs, class... Args>
+inline cudaError_t dr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = dr_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // counter-based keep/drop decision for dropout (keep prob 0.5, network/slim/ops.py:711).
 // Same splitmix64 finaliser as oracle/um_v1_torch.py:dropout_mask so masks are reproducible.

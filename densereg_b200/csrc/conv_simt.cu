@@ -21,6 +21,7 @@ struct PixCoord { int base; int iy0; int ix0; };   // base = b*H*W (pixel units)
 template <bool VEC4>
 __global__ void __launch_bounds__(NT)
 conv_fwd_kernel(ConvProblem p) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -170,6 +171,7 @@ constexpr int WK = 64, WN = 64, WM = 16;
 
 __global__ void __launch_bounds__(NT)
 conv_wgrad_kernel(WgradProblem p, int m_per_block) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ __align__(16) float As[2][WM][WK];
   __shared__ __align__(16) float Bs[2][WM][WN];
   const int tid = threadIdx.x;
@@ -276,8 +278,8 @@ int launch_conv_simt(const ConvProblem& p, cudaStream_t st) {
   const int M = p.B * p.Ho * p.Wo;
   dim3 grid((M + BM - 1) / BM, (p.Cout + BN - 1) / BN);
   const bool vec = (p.Cin % 4 == 0) && (p.x_cs % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
-  if (vec) conv_fwd_kernel<true><<<grid, NT, 0, st>>>(p);
-  else conv_fwd_kernel<false><<<grid, NT, 0, st>>>(p);
+  if (vec) dr_launch(conv_fwd_kernel<true>, dim3(grid), dim3(NT), 0, st, p);
+  else dr_launch(conv_fwd_kernel<false>, dim3(grid), dim3(NT), 0, st, p);
   return 1;
 }
 
@@ -295,6 +297,6 @@ int launch_wgrad_simt(const WgradProblem& p, cudaStream_t st) {
   int m_per_block = ((M + splits - 1) / splits + WM - 1) / WM * WM;
   splits = (M + m_per_block - 1) / m_per_block;
   dim3 grid(gx, gy, splits);
-  conv_wgrad_kernel<<<grid, NT, 0, st>>>(p, m_per_block);
+  dr_launch(conv_wgrad_kernel, dim3(grid), dim3(NT), 0, st, p, m_per_block);
   return 1;
 }

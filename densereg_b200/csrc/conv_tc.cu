@@ -34,6 +34,7 @@ template <bool SPLIT3>
 __global__ void __launch_bounds__(TC1_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.BN * TC_BK * 4;
@@ -69,6 +70,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // everything above (barriers, tensor-memory allocation) overlapped the previous kernel's tail
 
   if (warp < TC1_WARP_SPLIT0) {
   DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
@@ -319,11 +321,11 @@ int launch_conv_tc(const ConvProblem& p, int split3, cudaStream_t st) {
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (split3) {
     if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[1] = true; }
-    conv_tc_kernel<true><<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+    dr_launch(conv_tc_kernel<true>, dim3(grid), dim3(TC1_THREADS), smem_bytes, st, ma, mw, mwlo, t);
     return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<3xTF32>") ? 1 : 0;
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536); attr_set[0] = true; }
-    conv_tc_kernel<false><<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+    dr_launch(conv_tc_kernel<false>, dim3(grid), dim3(TC1_THREADS), smem_bytes, st, ma, mw, mwlo, t);
   }
   return launch_ok(cudaPeekAtLastError(), "conv_tc_kernel<TF32>") ? 1 : 0;
 }

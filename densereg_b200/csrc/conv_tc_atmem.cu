@@ -48,6 +48,7 @@ DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, 
 __global__ void __launch_bounds__(TC1_THREADS, 1)
 conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.BN * TC_BK * 4;
@@ -80,6 +81,7 @@ conv_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // everything above (barriers, tensor-memory allocation) overlapped the previous kernel's tail
 
   if (warp < TC1_WARP_SPLIT0) {
   DR_SETMAXNREG_DEC(REG_CTRL);                           // warpgroup 0 (control): hand registers to the epilogue warpgroup
@@ -295,6 +297,6 @@ int launch_conv_tc_atmem(const ConvProblem& p, cudaStream_t st) {
     if (cudaFuncSetAttribute(conv_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget + 1536) != cudaSuccess) return 0;
     attr_set = true;
   }
-  conv_tc_atmem_kernel<<<grid, TC1_THREADS, smem_bytes, st>>>(ma, mw, mwlo, t);
+  dr_launch(conv_tc_atmem_kernel, dim3(grid), dim3(TC1_THREADS), smem_bytes, st, ma, mw, mwlo, t);
   return 1;
 }

@@ -68,6 +68,7 @@ DR_DEVINL void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
 __global__ void __launch_bounds__(192 + SPLIT_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bh_bytes = (p.BN / 2) * TC_BK * 4;                   // this CTA's half of one weight tile (hi or lo)
@@ -108,6 +109,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   cluster_sync_all();          // barriers of both CTAs are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // everything above overlapped the previous kernel's tail (common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -309,9 +311,11 @@ int launch_conv_tc_pair(const ConvProblem& p, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(192 + SPLIT_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = dr_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   return tc::launch_ok(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, ma, mw, mwlo, t), "conv_tc_pair_kernel") ? 1 : 0;
 }

@@ -16,6 +16,15 @@
 #include <string>
 #include <vector>
 
+// programmatic dependent launch switch (common.cuh): DENSEREG_PDL=0 turns it off; suspended while a CUDA graph is being captured
+static int g_pdl_suspend = 0;
+bool dr_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DENSEREG_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1 && g_pdl_suspend == 0;
+}
+void dr_pdl_suspend(int on) { g_pdl_suspend = on; }
+
 namespace {
 
 struct Layer {
@@ -411,6 +420,7 @@ struct Builder {
 // ---------------------------------------------------------------------------------------------
 __global__ void fold_all_kernel(const LayerDev* __restrict__ t, const float* __restrict__ params, const float* __restrict__ state,
                                 float* __restrict__ aff) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   const LayerDev L = t[blockIdx.x];
   const float* pb = params + L.p_off;
   float* a = aff + L.aff_off;
@@ -717,7 +727,7 @@ int forward_impl(dr_handle* h, int B, const float* dm_mm, const float* coms, int
     CUDA_TRY(h, cudaMemsetAsync(h->sums, 0, h->n_sums * sizeof(double), st));
     CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, h->layers.size() * sizeof(unsigned int), st));
   } else {
-    fold_all_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state, h->aff); ++nl;
+    dr_launch(fold_all_kernel, dim3((unsigned)h->layers.size()), dim3(128), 0, st, h->ltab, h->params, h->state, h->aff); ++nl;
   }
   LaneCtx lanes{h, st0, h->lanes_on, &h->plan_fwd, &h->ev_fwd, {}};
   rc = lanes.begin();
@@ -1274,7 +1284,9 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
     if (!h->capture_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamSynchronize(st));               // the eager warm-up on `st` is done before the internal stream touches the arena
     CUDA_TRY(h, cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+    dr_pdl_suspend(1);                                    // plain kernel nodes inside the graph
     int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, h->capture_stream);
+    dr_pdl_suspend(0);
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
     if (rc || ce != cudaSuccess || !graph) {

@@ -30,6 +30,7 @@ inline int blocks_for(size_t n, int per_block = EW_T, int cap = 148 * 16) {
 
 __global__ void norm_dm_kernel(int B, int npix, const float* __restrict__ dm, const float* __restrict__ coms,
                                float* __restrict__ out) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = (size_t)B * npix;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int b = (int)(i / npix);
@@ -43,6 +44,7 @@ __global__ void norm_dm_kernel(int B, int npix, const float* __restrict__ dm, co
 
 __global__ void make_uvd_kernel(int B, int in_hw, int out_hw, const float* __restrict__ x0, float* __restrict__ tiny,
                                 UvdDst dst) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = (size_t)B * out_hw * out_hw;
   int s = in_hw / out_hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -63,6 +65,7 @@ __global__ void make_uvd_kernel(int B, int in_hw, int out_hw, const float* __res
 // SAME max pool stride 2: k=2 (pad 0,0) or k=3 (pad 0 before, 1 after on even inputs); padding never wins
 __global__ void maxpool_kernel(int B, int H, int W, int C, int k, const float* __restrict__ x, int x_cs,
                                float* __restrict__ y, int y_cs) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   int Ho = H / 2, Wo = W / 2;
   size_t n = (size_t)B * Ho * Wo * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -89,6 +92,7 @@ __global__ void maxpool_kernel(int B, int H, int W, int C, int k, const float* _
 // Default since round 2 (verified against the fp32 engine and measured: profiles/r2_sweep.md); DENSEREG_POOL_BWD_V4=0 selects the scalar kernel.
 __global__ void maxpool_bwd_v4_kernel(int B, int H, int W, int C4, int k, const float4* __restrict__ x, int x_cs4,
                                       const float4* __restrict__ dy, int dy_cs4, float4* __restrict__ dx, int dx_cs4, int accumulate) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   const int Ho = H / 2, Wo = W / 2;
   const size_t n = (size_t)B * H * W * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -129,6 +133,7 @@ __global__ void maxpool_bwd_v4_kernel(int B, int H, int W, int C4, int k, const 
 
 __global__ void maxpool_bwd_kernel(int B, int H, int W, int C, int k, const float* __restrict__ x, int x_cs,
                                    const float* __restrict__ dy, int dy_cs, float* __restrict__ dx, int dx_cs, int accumulate) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   int Ho = H / 2, Wo = W / 2;
   size_t n = (size_t)B * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -159,6 +164,7 @@ __global__ void maxpool_bwd_kernel(int B, int H, int W, int C, int k, const floa
 
 __global__ void upadd_kernel(int B, int H, int W, int C, const float* __restrict__ a, int a_cs,
                              const float* __restrict__ lo, int lo_cs, float* __restrict__ y, int y_cs) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = (size_t)B * H * W * C;
   int Hl = H / 2, Wl = W / 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -171,6 +177,7 @@ __global__ void upadd_kernel(int B, int H, int W, int C, const float* __restrict
 
 __global__ void upadd_bwd_lo_kernel(int B, int H, int W, int C, const float* __restrict__ dy, int dy_cs,
                                     float* __restrict__ dlo, int dlo_cs, int accumulate) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   int Hl = H / 2, Wl = W / 2;
   size_t n = (size_t)B * Hl * Wl * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -186,6 +193,7 @@ __global__ void upadd_bwd_lo_kernel(int B, int H, int W, int C, const float* __r
 
 __global__ void copy_view_kernel(size_t npix, int C, const float* __restrict__ src, int src_cs, float* __restrict__ dst,
                                  int dst_cs, int accumulate, const float* __restrict__ tiny_mask) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = npix * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C); size_t pix = i / C;
@@ -197,6 +205,7 @@ __global__ void copy_view_kernel(size_t npix, int C, const float* __restrict__ s
 }
 
 __global__ void fill_view_kernel(size_t npix, int C, float* __restrict__ dst, int dst_cs, float v) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = npix * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C); size_t pix = i / C;
@@ -210,6 +219,7 @@ __global__ void fill_view_kernel(size_t npix, int C, float* __restrict__ dst, in
 __global__ void channel_stats_finalize_kernel(size_t npix, int C, const float* __restrict__ x, int x_cs, double* __restrict__ sums,
                                               unsigned int* __restrict__ counter, const float* __restrict__ bg, float* __restrict__ state,
                                               float* __restrict__ aff, float* __restrict__ bstat, int update_state) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ double s1[8][33], s2[8][33];
   __shared__ int is_last;
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -239,6 +249,7 @@ __global__ void channel_stats_finalize_kernel(size_t npix, int C, const float* _
 
 __global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ raw, int raw_cs, const float* __restrict__ aff,
                                  int relu, const float* __restrict__ res, int res_cs, float* __restrict__ y, int y_cs) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = npix * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C); size_t pix = i / C;
@@ -253,6 +264,7 @@ __global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ r
 __global__ void brn_apply_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ raw, unsigned raw_cs4,
                                     const float4* __restrict__ aff, int relu, const float4* __restrict__ res, unsigned res_cs4,
                                     float4* __restrict__ y, unsigned y_cs4) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned pix = i / C4, c = i - pix * C4;
     const float4 x = raw[(size_t)pix * raw_cs4 + c], a = __ldg(aff + c), b = __ldg(aff + C4 + c);
@@ -266,6 +278,7 @@ __global__ void brn_apply_v4_kernel(unsigned n4, unsigned C4, const float4* __re
 __global__ void brn_bwd_reduce_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ raw,
                                       int raw_cs, const float* __restrict__ aff, const float* __restrict__ bstat, int relu,
                                       double* __restrict__ sums) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ double s1[8][33], s2[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
@@ -291,6 +304,7 @@ __global__ void brn_bwd_apply_kernel(size_t npix, int C, const float* __restrict
                                      int raw_cs, const float* __restrict__ aff, const float* __restrict__ bstat,
                                      const float* __restrict__ bg, int relu, const double* __restrict__ sums,
                                      float* __restrict__ draw, int draw_cs, float* __restrict__ gparam) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   size_t n = npix * C;
   const double inv_n = 1.0 / (double)npix;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -329,6 +343,7 @@ DR_DEVINL void brn_quad_load(BrnQuad& q, const float* __restrict__ aff, const fl
 __global__ void brn_bwd_reduce_v4_kernel(unsigned npix, unsigned C4, const float4* __restrict__ dy, unsigned dy_cs4,
                                          const float4* __restrict__ raw, unsigned raw_cs4, const float* __restrict__ aff,
                                          const float* __restrict__ bstat, int relu, double* __restrict__ sums) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   extern __shared__ double red[];                       // [2][blockDim.x][4]
   const unsigned lanes = blockDim.x / C4, cq = threadIdx.x % C4, pl = threadIdx.x / C4;
   const int C = (int)C4 * 4, c = (int)cq * 4;
@@ -379,6 +394,7 @@ __global__ void brn_bwd_apply_v4_kernel(unsigned npix, unsigned C4, const float4
                                         const float* __restrict__ bstat, const float* __restrict__ bg, int relu,
                                         const double* __restrict__ sums, float4* __restrict__ draw, unsigned draw_cs4,
                                         float* __restrict__ gparam) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   const unsigned lanes = blockDim.x / C4, cq = threadIdx.x % C4, pl = threadIdx.x / C4;
   const int C = (int)C4 * 4, c = (int)cq * 4;
   const double inv_n = 1.0 / (double)npix;
@@ -425,6 +441,7 @@ __global__ void brn_bwd_apply_v4_kernel(unsigned npix, unsigned C4, const float4
 // float4 copy / accumulate of a view (optional depth mask)
 __global__ void copy_view_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ src, unsigned src_cs4, float4* __restrict__ dst,
                                     unsigned dst_cs4, int accumulate, const float* __restrict__ tiny_mask) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned pix = i / C4, c = i - pix * C4;
     float4 v = src[(size_t)pix * src_cs4 + c];
@@ -437,6 +454,7 @@ __global__ void copy_view_v4_kernel(unsigned n4, unsigned C4, const float4* __re
 
 __global__ void bias_bwd_kernel(size_t npix, int C, const float* __restrict__ dy, int dy_cs, const float* __restrict__ out, int out_cs,
                                 int relu, int dropout, float* __restrict__ dz, int dz_cs, float* __restrict__ gbias) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ float s1[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -460,6 +478,7 @@ __global__ void bias_bwd_kernel(size_t npix, int C, const float* __restrict__ dy
 // one pixel, so the hm / hm3 rows (J floats) and the um row (3J floats) are read and written contiguously.  (The first version looped over
 // the joints inside one thread per pixel: 40960 threads for batch 40, 101 us for 52 MB of traffic.)
 __global__ void loss_kernel(LossArgs a) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   const int hw = a.hw, J = a.J;
   const size_t n = (size_t)a.B * hw * hw * J;
   double l_hm = 0.0, l_hm3 = 0.0, l_um = 0.0;
@@ -516,6 +535,7 @@ __global__ void loss_kernel(LossArgs a) {
 }
 
 __global__ void wd_kernel(size_t n, const float* __restrict__ p, const float* __restrict__ wdm, float* __restrict__ g, double* __restrict__ reg) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   double acc = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float w = wdm[i];
@@ -529,6 +549,7 @@ __global__ void wd_kernel(size_t n, const float* __restrict__ p, const float* __
 }
 
 __global__ void finish_loss_kernel(const double* __restrict__ acc, float* __restrict__ out5) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   double t = acc[0] + acc[1] + acc[2] + acc[3];
   out5[0] = (float)t; out5[1] = (float)acc[0]; out5[2] = (float)acc[1]; out5[3] = (float)acc[2]; out5[4] = (float)acc[3];
 }
@@ -578,17 +599,17 @@ __global__ void gather_outputs_kernel(size_t npix, int C, const float* __restric
 
 int launch_norm_dm(int B, int hw, const float* dm, const float* coms, float* out, cudaStream_t st) {
   size_t n = (size_t)B * hw * hw;
-  norm_dm_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, hw * hw, dm, coms, out);
+  dr_launch(norm_dm_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, hw * hw, dm, coms, out);
   return 1;
 }
 int launch_make_uvd(int B, int in_hw, int out_hw, const float* x0, float* tiny, UvdDst dst, cudaStream_t st) {
   size_t n = (size_t)B * out_hw * out_hw;
-  make_uvd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, in_hw, out_hw, x0, tiny, dst);
+  dr_launch(make_uvd_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, in_hw, out_hw, x0, tiny, dst);
   return 1;
 }
 int launch_maxpool(int B, int H, int W, int C, int k, const float* x, int x_cs, float* y, int y_cs, cudaStream_t st) {
   size_t n = (size_t)B * (H / 2) * (W / 2) * C;
-  maxpool_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, k, x, x_cs, y, y_cs);
+  dr_launch(maxpool_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, H, W, C, k, x, x_cs, y, y_cs);
   return 1;
 }
 int launch_maxpool_bwd(int B, int H, int W, int C, int k, const float* x, int x_cs, const float* dy, int dy_cs,
@@ -598,21 +619,21 @@ int launch_maxpool_bwd(int B, int H, int W, int C, int k, const float* x, int x_
   if (v4 < 0) { const char* e = getenv("DENSEREG_POOL_BWD_V4"); v4 = (e && e[0] == '0') ? 0 : 1; }   // default on: -0.36 ms per micro-batch (profiles/r2_sweep.md)
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (v4 && C % 4 == 0 && x_cs % 4 == 0 && dy_cs % 4 == 0 && dx_cs % 4 == 0 && al(x) && al(dy) && al(dx)) {
-    maxpool_bwd_v4_kernel<<<blocks_for(n / 4), EW_T, 0, st>>>(B, H, W, C / 4, k, (const float4*)x, x_cs / 4, (const float4*)dy, dy_cs / 4,
+    dr_launch(maxpool_bwd_v4_kernel, dim3(blocks_for(n / 4)), dim3(EW_T), 0, st, B, H, W, C / 4, k, (const float4*)x, x_cs / 4, (const float4*)dy, dy_cs / 4,
                                                               (float4*)dx, dx_cs / 4, accumulate);
     return 1;
   }
-  maxpool_bwd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, k, x, x_cs, dy, dy_cs, dx, dx_cs, accumulate);
+  dr_launch(maxpool_bwd_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, H, W, C, k, x, x_cs, dy, dy_cs, dx, dx_cs, accumulate);
   return 1;
 }
 int launch_upadd(int B, int H, int W, int C, const float* a, int a_cs, const float* lo, int lo_cs, float* y, int y_cs, cudaStream_t st) {
   size_t n = (size_t)B * H * W * C;
-  upadd_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, a, a_cs, lo, lo_cs, y, y_cs);
+  dr_launch(upadd_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, H, W, C, a, a_cs, lo, lo_cs, y, y_cs);
   return 1;
 }
 int launch_upadd_bwd_lo(int B, int H, int W, int C, const float* dy, int dy_cs, float* dlo, int dlo_cs, int accumulate, cudaStream_t st) {
   size_t n = (size_t)B * (H / 2) * (W / 2) * C;
-  upadd_bwd_lo_kernel<<<blocks_for(n), EW_T, 0, st>>>(B, H, W, C, dy, dy_cs, dlo, dlo_cs, accumulate);
+  dr_launch(upadd_bwd_lo_kernel, dim3(blocks_for(n)), dim3(EW_T), 0, st, B, H, W, C, dy, dy_cs, dlo, dlo_cs, accumulate);
   return 1;
 }
 int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* dst, int dst_cs, int accumulate,
@@ -620,14 +641,14 @@ int launch_copy_view(size_t npix, int C, const float* src, int src_cs, float* ds
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (C % 4 == 0 && src_cs % 4 == 0 && dst_cs % 4 == 0 && al(src) && al(dst) && npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
     const unsigned n4 = (unsigned)(npix * (C / 4));
-    copy_view_v4_kernel<<<blocks_for(n4), EW_T, 0, st>>>(n4, C / 4, (const float4*)src, src_cs / 4, (float4*)dst, dst_cs / 4, accumulate, tiny_mask);
+    dr_launch(copy_view_v4_kernel, dim3(blocks_for(n4)), dim3(EW_T), 0, st, n4, C / 4, (const float4*)src, src_cs / 4, (float4*)dst, dst_cs / 4, accumulate, tiny_mask);
   } else {
-    copy_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, src, src_cs, dst, dst_cs, accumulate, tiny_mask);
+    dr_launch(copy_view_kernel, dim3(blocks_for(npix * C)), dim3(EW_T), 0, st, npix, C, src, src_cs, dst, dst_cs, accumulate, tiny_mask);
   }
   return 1;
 }
 int launch_fill_view(size_t npix, int C, float* dst, int dst_cs, float v, cudaStream_t st) {
-  fill_view_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dst, dst_cs, v);
+  dr_launch(fill_view_kernel, dim3(blocks_for(npix * C)), dim3(EW_T), 0, st, npix, C, dst, dst_cs, v);
   return 1;
 }
 static dim3 stats_grid(size_t npix, int C) {
@@ -640,7 +661,7 @@ static dim3 stats_grid(size_t npix, int C) {
 }
 int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, double* sums, unsigned int* counter,
                                   const float* beta_gamma, float* state, float* aff, float* bstat, int update_state, cudaStream_t st) {
-  channel_stats_finalize_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, x, x_cs, sums, counter, beta_gamma, state, aff, bstat,
+  dr_launch(channel_stats_finalize_kernel, dim3(stats_grid(npix, C)), dim3(dim3(32, 8)), 0, st, npix, C, x, x_cs, sums, counter, beta_gamma, state, aff, bstat,
                                                                             update_state);
   return 1;
 }
@@ -650,10 +671,10 @@ int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const flo
   if (C % 4 == 0 && raw_cs % 4 == 0 && y_cs % 4 == 0 && (!res || res_cs % 4 == 0) && al(raw) && al(y) && al(aff) && (!res || al(res)) &&
       npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
     const unsigned n4 = (unsigned)(npix * (C / 4));
-    brn_apply_v4_kernel<<<blocks_for(n4), EW_T, 0, st>>>(n4, C / 4, (const float4*)raw, raw_cs / 4, (const float4*)aff, relu,
+    dr_launch(brn_apply_v4_kernel, dim3(blocks_for(n4)), dim3(EW_T), 0, st, n4, C / 4, (const float4*)raw, raw_cs / 4, (const float4*)aff, relu,
                                                         (const float4*)res, res_cs / 4, (float4*)y, y_cs / 4);
   } else {
-    brn_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
+    dr_launch(brn_apply_kernel, dim3(blocks_for(npix * C)), dim3(EW_T), 0, st, npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
   }
   return 1;
 }
@@ -682,11 +703,11 @@ int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const 
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   unsigned block, grid;
   if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid, 148)) {
-    brn_bwd_reduce_v4_kernel<<<grid, block, (size_t)block * 4 * 2 * sizeof(double), st>>>((unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4,
+    dr_launch(brn_bwd_reduce_v4_kernel, dim3(grid), dim3(block), (size_t)block * 4 * 2 * sizeof(double), st, (unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4,
                                                                                         (const float4*)raw, raw_cs / 4, aff, bstat, relu, sums);
     return 1;
   }
-  brn_bwd_reduce_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, relu, sums);
+  dr_launch(brn_bwd_reduce_kernel, dim3(stats_grid(npix, C)), dim3(dim3(32, 8)), 0, st, npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, relu, sums);
   return 1;
 }
 int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
@@ -695,30 +716,30 @@ int launch_brn_bwd_apply(size_t npix, int C, const float* dy, int dy_cs, const f
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   unsigned block, grid;
   if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && draw_cs % 4 == 0 && al(raw) && al(dy) && al(draw) && brn_v4_shape(npix, C, &block, &grid, 148 * 8)) {
-    brn_bwd_apply_v4_kernel<<<grid, block, 0, st>>>((unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4, (const float4*)raw, raw_cs / 4, aff,
+    dr_launch(brn_bwd_apply_v4_kernel, dim3(grid), dim3(block), 0, st, (unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4, (const float4*)raw, raw_cs / 4, aff,
                                                     bstat, beta_gamma, relu, sums, (float4*)draw, draw_cs / 4, gparam);
   } else {
-    brn_bwd_apply_kernel<<<blocks_for(npix * C), EW_T, 0, st>>>(npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, beta_gamma, relu,
+    dr_launch(brn_bwd_apply_kernel, dim3(blocks_for(npix * C)), dim3(EW_T), 0, st, npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, beta_gamma, relu,
                                                                 sums, draw, draw_cs, gparam);
   }
   return 1;
 }
 int launch_bias_bwd(size_t npix, int C, const float* dy, int dy_cs, const float* out, int out_cs, int relu, int dropout,
                     float* dz, int dz_cs, float* gbias, cudaStream_t st) {
-  bias_bwd_kernel<<<stats_grid(npix, C), dim3(32, 8), 0, st>>>(npix, C, dy, dy_cs, out, out_cs, relu, dropout, dz, dz_cs, gbias);
+  dr_launch(bias_bwd_kernel, dim3(stats_grid(npix, C)), dim3(dim3(32, 8)), 0, st, npix, C, dy, dy_cs, out, out_cs, relu, dropout, dz, dz_cs, gbias);
   return 1;
 }
 int launch_loss(const LossArgs& a, cudaStream_t st) {
   size_t n = (size_t)a.B * a.hw * a.hw * a.J;
-  loss_kernel<<<blocks_for(n, EW_T * 2, 148 * 8), EW_T, 0, st>>>(a);
+  dr_launch(loss_kernel, dim3(blocks_for(n, EW_T * 2, 148 * 8)), dim3(EW_T), 0, st, a);
   return 1;
 }
 int launch_wd(size_t n, const float* params, const float* wdmask, float* grads, double* reg_acc, cudaStream_t st) {
-  wd_kernel<<<blocks_for(n, EW_T * 4, 148 * 4), EW_T, 0, st>>>(n, params, wdmask, grads, reg_acc);
+  dr_launch(wd_kernel, dim3(blocks_for(n, EW_T * 4, 148 * 4)), dim3(EW_T), 0, st, n, params, wdmask, grads, reg_acc);
   return 1;
 }
 int launch_finish_loss(const double* acc, float* out5, cudaStream_t st) {
-  finish_loss_kernel<<<1, 1, 0, st>>>(acc, out5);
+  dr_launch(finish_loss_kernel, dim3(1), dim3(1), 0, st, acc, out5);
   return 1;
 }
 int launch_adam(size_t n, float* p, const float* g, float* m, float* v, float divisor, float clip,

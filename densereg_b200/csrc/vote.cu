@@ -63,6 +63,7 @@ DR_DEVINL int f2i_trunc_sat(float v) {
 
 __global__ void __launch_bounds__(VOTE_MAX_THREADS)
 vote_kernel(VoteParams a) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   __shared__ float s_sc[VOTE_MAX_THREADS * VOTE_K];
   __shared__ int s_ix[VOTE_MAX_THREADS * VOTE_K];
   const int b = blockIdx.x;
@@ -251,6 +252,6 @@ int launch_vote(int B, int H, int W, int J,
   int threads = a.G * J;
   threads = (threads + 31) / 32 * 32;
   if (threads > VOTE_MAX_THREADS) threads = VOTE_MAX_THREADS;
-  vote_kernel<<<B, threads, 0, st>>>(a);
+  dr_launch(vote_kernel, dim3(B), dim3(threads), 0, st, a);
   return 1;
 }

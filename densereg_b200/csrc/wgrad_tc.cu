@@ -42,6 +42,7 @@ struct WgParams {
 template <bool SPLIT3>
 __global__ void __launch_bounds__(SPLIT3 ? 192 + WG_SPLIT_THREADS : 192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.nchunks_b * WG_CHUNK_BYTES;
@@ -74,6 +75,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // everything above (barriers, tensor-memory allocation) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -224,6 +226,7 @@ DR_DEVINL void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, 
 
 __global__ void __launch_bounds__(192 + WG_SPLIT_THREADS, 1)
 wgrad_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.nchunks_b * WG_CHUNK_BYTES;
@@ -253,6 +256,7 @@ wgrad_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // everything above (barriers, tensor-memory allocation) overlapped the previous kernel's tail
 
   struct Item { int tap, c0, n0, kb_begin, num_kb; };
   auto decode = [&](int item) {
@@ -514,17 +518,17 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
       const int total_items = tiles * splits;
       const size_t asmem = (size_t)a_stages * a_stage + (3 * a_stages + 4) * 8 + 16 + 1024 + 64;
       if (!aattr) { cudaFuncSetAttribute(wgrad_tc_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); aattr = true; }
-      wgrad_tc_atmem_kernel<<<dim3(total_items < num_sms_a ? total_items : num_sms_a), 192 + WG_SPLIT_THREADS, asmem, st>>>(mx, mdy, ta);
+      dr_launch(wgrad_tc_atmem_kernel, dim3(dim3(total_items < num_sms_a ? total_items : num_sms_a)), dim3(192 + WG_SPLIT_THREADS), asmem, st, mx, mdy, ta);
       return launch_ok(cudaPeekAtLastError(), "wgrad_tc_atmem_kernel") ? 1 : 0;
     }
   }
   dim3 grid(t.cin_tiles * p.k * p.k, cout_tiles, splits);
   if (split3) {
     if (!attr_set[1]) { cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[1] = true; }
-    wgrad_tc_kernel<true><<<grid, 192 + WG_SPLIT_THREADS, smem_bytes, st>>>(mx, mdy, t);
+    dr_launch(wgrad_tc_kernel<true>, dim3(grid), dim3(192 + WG_SPLIT_THREADS), smem_bytes, st, mx, mdy, t);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); attr_set[0] = true; }
-    wgrad_tc_kernel<false><<<grid, 192, smem_bytes, st>>>(mx, mdy, t);
+    dr_launch(wgrad_tc_kernel<false>, dim3(grid), dim3(192), smem_bytes, st, mx, mdy, t);
   }
   return launch_ok(cudaPeekAtLastError(), "wgrad_tc_kernel") ? 1 : 0;
 }

@@ -5,17 +5,15 @@ Each child checks the training micro-step against the fp32 FFMA engine (GPU vs G
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
-CONFIGS = [   # round-2 fifth pass: setmaxnreg role layout, register-resident running sums, two splitter warpgroups in the A-TMEM conv kernel
+CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("base", {}),
-    ("split_groups_1", {"DENSEREG_TC_SPLIT_GROUPS": "1"}),
-    ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
-    ("a_tmem_0", {"DENSEREG_TC_A_TMEM": "0"}),
-    ("pair_mincout_64", {"DENSEREG_TC_PAIR_MINCOUT": "64"}),
-    ("pair_mincout_80", {"DENSEREG_TC_PAIR_MINCOUT": "80"}),
-    ("pair_mincout_64_w", {"DENSEREG_TC_PAIR_MINCOUT": "64", "DENSEREG_TC_PAIR_MINWORK": "0"}),
-    ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
+    ("no_pdl", {"DENSEREG_PDL": "0"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
+    ("no_lanes_no_pdl", {"DENSEREG_LANES": "0", "DENSEREG_PDL": "0"}),
+    ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
+    ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
 ]
+EXTRA = [a for a in os.environ.get("SWEEP_ARGS", "").split() if a]     # e.g. SWEEP_ARGS="--batch 8 --J 14"
 want = set(sys.argv[1:])
 path = os.path.join(OUT, "r2_sweep.jsonl")
 for name, env in CONFIGS:
@@ -23,7 +21,7 @@ for name, env in CONFIGS:
         continue
     e = dict(os.environ, **env)
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_check.py"), "--tag", name], env=e, capture_output=True, text=True,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_check.py"), "--tag", name] + EXTRA, env=e, capture_output=True, text=True,
                            timeout=int(os.environ.get("SWEEP_TIMEOUT", "150")))
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         rec = json.loads(line[-1]) if line else {"tag": name, "error": "no output", "stderr": r.stderr[-800:], "rc": r.returncode}
