@@ -1284,7 +1284,9 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
     if (!h->capture_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamSynchronize(st));               // the eager warm-up on `st` is done before the internal stream touches the arena
     CUDA_TRY(h, cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    dr_pdl_suspend(1);                                    // plain kernel nodes inside the graph
+    static int pdl_graph = -1;                            // DENSEREG_PDL_GRAPH=1: keep the programmatic edges inside the captured graph
+    if (pdl_graph < 0) { const char* e = getenv("DENSEREG_PDL_GRAPH"); pdl_graph = (e && e[0] == '1') ? 1 : 0; }
+    if (!pdl_graph) dr_pdl_suspend(1);                    // plain kernel nodes inside the graph
     int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, h->capture_stream);
     dr_pdl_suspend(0);
     cudaGraph_t graph = nullptr;
