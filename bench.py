@@ -36,7 +36,7 @@ METRICS = {"train": "depth-crops/sec (128x128, 2-stack fea=128) training step", 
            "vote": "depth-crops/sec offset-vote (128x128 maps, J=21)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels named in `roofline`, from the `ncu --set full` captures summarised
 # under profiles/ (r1_final.md: CTA-pair conv on um_comb/c2 at B=40 = 46.8 MB read + 4.3 MB written; r2_*.md for wgrad); None = not captured
-NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": None}
+NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": 90.7e6}      # wgrad on um_comb/c2, B=40: 86.3 MB read + 4.4 MB written (profiles/r2_kernels.md)
 
 
 def measured_peaks():
@@ -431,20 +431,32 @@ def run_train(args, c):
     k_flops = 2.0 * B * 1024 * 9 * 256 * 256
     best = k_flops / (k_ms * 1e-3) / 1e12
     step_tflops = value / world * TRAIN_GFLOP_PER_CROP[J] / 1e3
-    top = classes[0] if classes else {"class": "conv", "achieved": best, "frac": best / peaks["bf16_burst"], "avg_launch_ms": k_ms, "launches": 0, "total_ms": 0}
-    roofline = {"bound": "tensor", "achieved": top["achieved"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": top["frac"],
-                "traffic": NCU_TRAFFIC_BYTES.get(top["class"]),
-                "kernel": "time-dominant kernel class of the step: %s (%d launches per micro-batch, %.2f ms = %.0f %% of the conv-type time; "
-                          "algorithmic FLOPs of all its launches / their summed launch times, each timed alone on its stream)"
-                          % (top["class"], top["launches"], top["total_ms"], 100.0 * top["total_ms"] / max(traced_ms, 1e-9)),
-                "avg_launch_ms": top["avg_launch_ms"],
-                "peak_source": peaks["src"] + " dense bf16 cuBLAS burst (tf32 kind is nominally half of bf16; 3xTF32 issues 3 MMAs per algorithmic MAC)",
-                "classes": classes,
-                "best_layer": {"kernel": "conv implicit GEMM (%s) on s0/um_comb/c2 3x3 256->256, B=%d, timed alone" % (args.precision, B),
+    top = classes[0] if classes else {"class": "wgrad", "achieved": 0.0, "frac": 0.0, "avg_launch_ms": 0.0, "launches": 0, "total_ms": 0.0}
+    # the time-dominant class (wgrad) on ITS heaviest layer, timed alone like best_layer: per-launch FLOPs / per-launch time, with the
+    # per-launch DRAM traffic of the same launch from the ncu capture
+    dyb = torch.randn(B, 32, 32, 256, device=dev)
+    for r in range(3):
+        eng.debug_conv_bwd(li, xs[r % 4], dyb, args.precision, want_dx=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for r in range(reps):
+        eng.debug_conv_bwd(li, xs[r % 4], dyb, args.precision, want_dx=False)
+    e1.record(); torch.cuda.synchronize()
+    w_ms = e0.elapsed_time(e1) / reps
+    w_ach = k_flops / (w_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": w_ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": w_ach / peaks["bf16_burst"],
+                "traffic": NCU_TRAFFIC_BYTES["wgrad"] if B == 40 and args.precision == "tf32x3" else None,
+                "kernel": "wgrad_tc_kernel (filter gradient) on its heaviest layer s0/um_comb/c2 3x3 256->256, B=%d, timed alone (includes the memset of the "
+                          "2.4 MB gradient).  wgrad is the TIME-DOMINANT kernel class of the step: %d launches per micro-batch, %.2f ms = %.0f %% of the "
+                          "conv-type time at %.0f TFLOP/s over all its layers (`classes`)"
+                          % (B, top["launches"] if top["class"] == "wgrad" else 0, top["total_ms"], 100.0 * top["total_ms"] / max(traced_ms, 1e-9), top["achieved"]),
+                "kernel_ms": w_ms, "algorithmic_bytes": 4.0 * B * 1024 * 256 * 2 + 4.0 * 9 * 256 * 256,
+                "peak_source": peaks["src"] + " dense bf16 cuBLAS burst (tf32 kind is nominally half of bf16; 3xTF32 issues 3 MMAs per algorithmic MAC: ceiling = peak / 6)",
+                "dominant_class": top["class"], "classes": classes,
+                "best_layer": {"kernel": "conv implicit GEMM (%s, CTA-pair kernel) on s0/um_comb/c2 3x3 256->256, B=%d, timed alone" % (args.precision, B),
                                "kernel_ms": k_ms, "achieved": best, "frac": best / peaks["bf16_burst"], "traffic": NCU_TRAFFIC_BYTES["conv"] if B == 40 else None},
                 "whole_step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"], "frac": step_tflops / peaks["bf16_sustained"],
                                "note": "%.2f GFLOP/crop (fwd+dgrad+wgrad conv FLOPs) x crops/s per GPU vs sustained measured peak" % TRAIN_GFLOP_PER_CROP[J]}}
-    roofline["kernel_ms"] = k_ms
 
     if rank == 0:
         cpu_baseline, mje = None, None
