@@ -29,7 +29,10 @@ class DrOpInfo(C.Structure):
                 ("in_buf", C.c_int32), ("in_c0", C.c_int32), ("in_c", C.c_int32),
                 ("out_buf", C.c_int32), ("out_c0", C.c_int32), ("out_c", C.c_int32),
                 ("res_buf", C.c_int32), ("res_c0", C.c_int32), ("res_c", C.c_int32),
-                ("nwait", C.c_int32 * 2), ("wait_op", (C.c_int32 * 3) * 2), ("record", C.c_int32 * 2)]
+                ("nwait", C.c_int32 * 2), ("wait_op", (C.c_int32 * 3) * 2), ("record", C.c_int32 * 2),
+                ("gsrc_buf", C.c_int32), ("gsrc_c0", C.c_int32), ("gsrc_c", C.c_int32),
+                ("dres_buf", C.c_int32), ("dres_c0", C.c_int32), ("dres_c", C.c_int32),
+                ("res_grad_fused", C.c_int32), ("in_grad_fused", C.c_int32)]
 
 
 class DrTraceRec(C.Structure):

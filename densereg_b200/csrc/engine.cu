@@ -64,6 +64,14 @@ struct Op {
   int k = 0;
   int need_dgrad = 1;
   GradWrite gw_in, gw_res;
+  // Gradient aliasing (backward): the gradient of a residual sum flows unchanged into both addends, so it is never copied --
+  //   gsrc            this op reads d(out) from that view instead of its own output's gradient (projection-skip conv: the block output's
+  //                   gradient; `upper1` block: the gradient of the hourglass level's upsample+add output)
+  //   dres            conv: d(dres) is ADDED in the dgrad epilogue as its residual operand (identity skip: d(block input) = dgrad(c1) + d(block output))
+  //   res_grad_fused  conv with a residual: no copy of d(out) into d(res) (the consumers above read d(out) directly)
+  //   in_grad_fused   upsample+add: no copy of d(out) into d(in)
+  View gsrc, dres;
+  int res_grad_fused = 0, in_grad_fused = 0;
 };
 
 }  // namespace
@@ -213,31 +221,41 @@ struct Builder {
     h->ops.push_back(o);
   }
   // skip_lane >= 0: the projection skip (if any) runs on that lane, next to the c1 -> c2 chain
-  void residual(const std::string& name, View in, int cin, int cout, View dest, int hw, int skip_lane = -1) {
+  struct ResOps { int c1, c3, skip; };
+  bool alias_grads = true;   // DENSEREG_GRAD_ALIAS=0: round-1 behaviour (copy the gradient of every residual sum)
+  ResOps residual(const std::string& name, View in, int cin, int cout, View dest, int hw, int skip_lane = -1) {
     int hc = cin / 2;
     int L1 = add_layer(name + "/c1", 1, 1, cin, hc, 1, 1, 0.0005f, hw);
     int L2 = add_layer(name + "/c2", 3, 1, hc, hc, 1, 1, 0.0005f, hw);
     int L3 = add_layer(name + "/c3", 1, 1, hc, cout, 1, 1, 0.0005f, hw);
     int Ls = cout != cin ? add_layer(name + "/skip", 1, 1, cin, cout, 1, 1, 0.0005f, hw) : -1;
     int t1 = new_buf(hw, hc), t2 = new_buf(hw, hc);
-    conv_op(L1, in, V(t1));
+    ResOps r{-1, -1, -1};
+    conv_op(L1, in, V(t1)); r.c1 = (int)h->ops.size() - 1;
     conv_op(L2, V(t1), V(t2));
     View sk = in;
     if (Ls >= 0) {
       int sb = new_buf(hw, cout);
       const int keep = cur_lane;
       if (skip_lane >= 0) cur_lane = skip_lane;
-      conv_op(Ls, in, V(sb)); sk = V(sb);
+      conv_op(Ls, in, V(sb)); sk = V(sb); r.skip = (int)h->ops.size() - 1;
       cur_lane = keep;
     }
-    conv_op(L3, V(t2), dest, sk);
+    conv_op(L3, V(t2), dest, sk); r.c3 = (int)h->ops.size() - 1;
+    if (alias_grads) {
+      h->ops[r.c3].res_grad_fused = 1;
+      if (r.skip >= 0) h->ops[r.skip].gsrc = dest;          // the skip conv back-propagates the block output's gradient directly
+      else h->ops[r.c1].dres = dest;                        // identity skip: added in c1's dgrad epilogue
+    }
+    return r;
   }
   void hourglass(const std::string& name, int n, View x, View dest, int hw) {
     char tag[16]; snprintf(tag, sizeof(tag), "/n%d", n);
     std::string p = name + tag;
     int up1 = new_buf(hw, F);
+    ResOps up;
     { const int keep = cur_lane; cur_lane = 1 + (n & 1);                      // the upper branch of level n overlaps the whole lower path
-      residual(p + "/upper1", x, F, F, V(up1), hw);
+      up = residual(p + "/upper1", x, F, F, V(up1), hw);
       cur_lane = keep; }
     int pl = new_buf(hw / 2, F);
     { Op o; o.kind = OP_POOL; o.lane = cur_lane; o.in = x; o.out = V(pl); o.k = 3; h->ops.push_back(o); }
@@ -247,9 +265,16 @@ struct Builder {
     if (n > 1) { low2 = new_buf(hw / 2, F); hourglass(name, n - 1, V(low1), V(low2), hw / 2); }
     int low3 = new_buf(hw / 2, F);
     residual(p + "/lower3", V(low2), F, F, V(low3), hw / 2);
-    { Op o; o.kind = OP_UPADD; o.lane = cur_lane; o.in = V(up1); o.res = V(low3); o.out = dest; h->ops.push_back(o); }
+    { Op o; o.kind = OP_UPADD; o.lane = cur_lane; o.in = V(up1); o.res = V(low3); o.out = dest;
+      if (alias_grads) {                                                      // d(up1) == d(dest): the upper1 block reads it in place
+        o.in_grad_fused = 1;
+        h->ops[up.c3].gsrc = dest;
+        h->ops[up.c1].dres = dest;                                            // (identity skip: F -> F)
+      }
+      h->ops.push_back(o); }
   }
   void build() {
+    { const char* e = getenv("DENSEREG_GRAD_ALIAS"); alias_grads = !(e && e[0] == '0'); }
     F = h->cfg.num_fea; J = h->cfg.num_jnt; S = h->cfg.num_stack;
     const int IN = h->cfg.in_hw, OUT = h->cfg.out_hw;
     h->buf_x0 = new_buf(IN, 1);
@@ -363,12 +388,14 @@ struct Builder {
     }, h->plan_fwd);
     // backward: gradient arena (buffer id + nb); forward activations are read-only here and complete before the pass starts
     plan_pass(bo, [&](const Op& o, std::vector<Access>& v) {
-      rd(v, nb + o.out.buf, o.out);
+      const View& gv = o.gsrc.buf >= 0 ? o.gsrc : o.out;
+      rd(v, nb + gv.buf, gv);
       if (o.kind == OP_CONV) {
-        if (o.res.buf >= 0) wr(v, nb + o.res.buf, o.res);
+        if (o.res.buf >= 0 && !o.res_grad_fused) wr(v, nb + o.res.buf, o.res);
+        if (o.dres.buf >= 0) rd(v, nb + o.dres.buf, o.dres);
         if (o.need_dgrad) wr(v, nb + o.in.buf, o.in);
       } else {
-        wr(v, nb + o.in.buf, o.in);
+        if (!(o.kind == OP_UPADD && o.in_grad_fused)) wr(v, nb + o.in.buf, o.in);
         if (o.kind == OP_UPADD) wr(v, nb + o.res.buf, o.res);
       }
     }, h->plan_bwd);
@@ -404,11 +431,11 @@ struct Builder {
       Op& o = h->ops[i];
       switch (o.kind) {
         case OP_CONV:
-          if (o.res.buf >= 0) o.gw_res = plan(o.res);
+          if (o.res.buf >= 0 && !o.res_grad_fused) o.gw_res = plan(o.res);
           if (o.need_dgrad) o.gw_in = plan(o.in);
           break;
         case OP_POOL: o.gw_in = plan(o.in); break;
-        case OP_UPADD: o.gw_in = plan(o.in); o.gw_res = plan(o.res); break;
+        case OP_UPADD: if (!o.in_grad_fused) o.gw_in = plan(o.in); o.gw_res = plan(o.res); break;
         case OP_MASKCOPY: o.gw_in = plan(o.in); break;
       }
     }
@@ -846,9 +873,10 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
     switch (o.kind) {
       case OP_CONV: {
         const Layer& L = h->layers[o.layer];
-        const float* dy = X.gptr(o.out); const int dy_cs = X.cs(o.out);
+        const View& gv = o.gsrc.buf >= 0 ? o.gsrc : o.out;          // gradient aliasing: see Op
+        const float* dy = X.gptr(gv); const int dy_cs = X.cs(gv);
         const size_t np = X.npix(o.out);
-        if (o.res.buf >= 0) {
+        if (o.res.buf >= 0 && !o.res_grad_fused) {
           nl += apply_fills(h, X, o.gw_res, st);
           nl += launch_copy_view(np, o.res.C, dy, dy_cs, X.gptr(o.res), X.cs(o.res), o.gw_res.acc, nullptr, st);
         }
@@ -887,6 +915,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
           p.pad_t = p.pad_l = L.k - 1 - same_pad_before(L.in_hw, L.k, L.stride);
           set_dgrad_weights(h, L, h->precision, p);
           p.y = X.gptr(o.in); p.y_cs = X.cs(o.in); p.accumulate = o.gw_in.acc;
+          if (o.dres.buf >= 0) { p.res = X.gptr(o.dres); p.res_cs = X.cs(o.dres); }      // identity skip: + d(block output)
           RUN_TRY(nl, run_conv(h, p, h->precision, st));
         }
         break;
@@ -900,8 +929,10 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
       }
       case OP_UPADD: {
         const Buf& bo = h->bufs[o.out.buf];
-        nl += apply_fills(h, X, o.gw_in, st);
-        nl += launch_copy_view(X.npix(o.out), o.out.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.in), X.cs(o.in), o.gw_in.acc, nullptr, st);
+        if (!o.in_grad_fused) {
+          nl += apply_fills(h, X, o.gw_in, st);
+          nl += launch_copy_view(X.npix(o.out), o.out.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.in), X.cs(o.in), o.gw_in.acc, nullptr, st);
+        }
         nl += apply_fills(h, X, o.gw_res, st);
         nl += launch_upadd_bwd_lo(B, bo.H, bo.W, o.out.C, X.gptr(o.out), X.cs(o.out), X.gptr(o.res), X.cs(o.res), o.gw_res.acc, st);
         break;
@@ -1132,7 +1163,8 @@ int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, vo
   Exec X{h, B, (cudaStream_t)stream};
   for (const Op& o : h->ops) {
     if (o.kind == OP_CONV && o.layer == layer) {
-      h->launches += launch_gather_outputs(X.npix(o.out), o.out.C, grad ? X.gptr(o.out) : X.ptr(o.out), X.cs(o.out), dst, X.st);
+      const View& gv = (grad && o.gsrc.buf >= 0) ? o.gsrc : o.out;
+      h->launches += launch_gather_outputs(X.npix(o.out), o.out.C, grad ? X.gptr(gv) : X.ptr(o.out), X.cs(gv), dst, X.st);
       CUDA_TRY(h, cudaGetLastError());
       return DR_OK;
     }
@@ -1162,6 +1194,9 @@ int dr_debug_op(const dr_handle* h, int idx, dr_op_info* out) {
   out->in_buf = o.in.buf; out->in_c0 = o.in.coff; out->in_c = o.in.C;
   out->out_buf = o.out.buf; out->out_c0 = o.out.coff; out->out_c = o.out.C;
   out->res_buf = o.res.buf; out->res_c0 = o.res.coff; out->res_c = o.res.C;
+  out->gsrc_buf = o.gsrc.buf; out->gsrc_c0 = o.gsrc.coff; out->gsrc_c = o.gsrc.C;
+  out->dres_buf = o.dres.buf; out->dres_c0 = o.dres.coff; out->dres_c = o.dres.C;
+  out->res_grad_fused = o.res_grad_fused; out->in_grad_fused = o.in_grad_fused;
   const OpPlan* pl[2] = {&h->plan_fwd[idx], &h->plan_bwd[idx]};
   for (int k = 0; k < 2; ++k) {
     out->nwait[k] = pl[k]->nwait; out->record[k] = pl[k]->record;
@@ -1284,8 +1319,8 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
     if (!h->capture_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamSynchronize(st));               // the eager warm-up on `st` is done before the internal stream touches the arena
     CUDA_TRY(h, cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    static int pdl_graph = -1;                            // DENSEREG_PDL_GRAPH=1: keep the programmatic edges inside the captured graph
-    if (pdl_graph < 0) { const char* e = getenv("DENSEREG_PDL_GRAPH"); pdl_graph = (e && e[0] == '1') ? 1 : 0; }
+    static int pdl_graph = -1;                            // programmatic edges are kept inside the captured graph (B=1: 1.68 -> 1.56 ms); DENSEREG_PDL_GRAPH=0: plain nodes
+    if (pdl_graph < 0) { const char* e = getenv("DENSEREG_PDL_GRAPH"); pdl_graph = (e && e[0] == '0') ? 0 : 1; }
     if (!pdl_graph) dr_pdl_suspend(1);                    // plain kernel nodes inside the graph
     int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, h->capture_stream);
     dr_pdl_suspend(0);

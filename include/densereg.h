@@ -214,6 +214,10 @@ typedef struct {
   int32_t out_buf, out_c0, out_c;
   int32_t res_buf, res_c0, res_c;   /* residual operand (conv) / low-resolution operand (upsample+add); buf < 0: none */
   int32_t nwait[2], wait_op[2][3], record[2];   /* [0] forward pass, [1] backward pass: ops (of other lanes) whose event this op waits for */
+  /* backward-pass gradient aliasing (the gradient of a residual sum is read in place, never copied): */
+  int32_t gsrc_buf, gsrc_c0, gsrc_c;            /* buf >= 0: d(out) is read from this view                                  */
+  int32_t dres_buf, dres_c0, dres_c;            /* buf >= 0: this view's gradient is added in the conv's dgrad epilogue     */
+  int32_t res_grad_fused, in_grad_fused;        /* no copy of d(out) into d(res) / d(in)                                    */
 } dr_op_info;
 DR_API int dr_num_ops(const dr_handle* h);
 DR_API int dr_debug_op(const dr_handle* h, int idx, dr_op_info* out);

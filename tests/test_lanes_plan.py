@@ -27,6 +27,9 @@ def _ops(lib, S, F, J):
         ops.append(dict(i=i, kind=o.kind, lane=o.lane, name=name, need_dgrad=o.need_dgrad, raw=o.raw_buf,
                         inn=(o.in_buf, o.in_c0, o.in_c0 + o.in_c), out=(o.out_buf, o.out_c0, o.out_c0 + o.out_c),
                         res=(o.res_buf, o.res_c0, o.res_c0 + o.res_c) if o.res_buf >= 0 else None,
+                        gsrc=(o.gsrc_buf, o.gsrc_c0, o.gsrc_c0 + o.gsrc_c) if o.gsrc_buf >= 0 else None,
+                        dres=(o.dres_buf, o.dres_c0, o.dres_c0 + o.dres_c) if o.dres_buf >= 0 else None,
+                        res_grad_fused=o.res_grad_fused, in_grad_fused=o.in_grad_fused,
                         waits=[[o.wait_op[p][k] for k in range(o.nwait[p])] for p in (0, 1)], record=[o.record[0], o.record[1]]))
     lib.dr_destroy(h)
     return ops
@@ -41,14 +44,17 @@ def _accesses(o, backward):
         if o["raw"] >= 0:
             acc.append(("a", o["raw"], 0, 1 << 20, True))
         return acc
-    acc = [("g", *o["out"], False)]
+    acc = [("g", *(o["gsrc"] or o["out"]), False)]           # gradient aliasing: d(out) may be read from another view
     if o["kind"] == CONV:
-        if o["res"]:
+        if o["res"] and not o["res_grad_fused"]:
             acc.append(("g", *o["res"], True))
+        if o["dres"]:
+            acc.append(("g", *o["dres"], False))
         if o["need_dgrad"]:
             acc.append(("g", *o["inn"], True))
     else:
-        acc.append(("g", *o["inn"], True))
+        if not (o["kind"] == UPADD and o["in_grad_fused"]):
+            acc.append(("g", *o["inn"], True))
         if o["kind"] == UPADD:
             acc.append(("g", *o["res"], True))
     return acc
@@ -99,3 +105,30 @@ def test_lane_assignment_follows_the_graph(built_lib):
     assert {o["lane"] for o in ops} == {0, 1, 2}
     lower = [o for o in ops if "/lower" in o["name"] or o["kind"] in (POOL, UPADD)]
     assert lower and all(o["lane"] == 0 for o in lower)
+
+
+@pytest.mark.parametrize("S,F,J", [(2, 128, 16), (1, 64, 14)])
+def test_backward_reads_only_written_gradients(built_lib, S, F, J):
+    """Gradient aliasing removed the copies of d(residual sum) (engine.cu: Op::gsrc / dres / *_grad_fused).  Walk the reverse schedule and check
+    that every gradient view an op reads has been completely written before -- by the loss kernel (the outputs hm / hm3 / um of every stack) or by
+    ops earlier in the walk -- and that the fused copies really are gone (no op writes the gradient of a skip buffer or of `up1`)."""
+    ops = _ops(built_lib, S, F, J)
+    written = {}
+    def mark(buf, c0, c1):
+        written.setdefault(buf, set()).update(range(c0, c1))
+    for o in ops:
+        if o["kind"] == CONV and o["name"].endswith(("/hm_out", "/hm3_out", "/um_out")):
+            mark(*o["out"])                                              # dL/d(output maps): loss_kernel
+    n_alias = 0
+    for o in reversed(ops):
+        for (_, buf, c0, c1, is_write) in _accesses(o, True):
+            if not is_write:
+                missing = set(range(c0, c1)) - written.get(buf, set())
+                assert not missing, "op %d (%s) reads an unwritten gradient: buffer %d channels %s" % (o["i"], o["name"], buf, sorted(missing)[:4])
+        for (_, buf, c0, c1, is_write) in _accesses(o, True):
+            if is_write:
+                mark(buf, c0, c1)
+        n_alias += int(o["gsrc"] is not None) + int(o["dres"] is not None)
+    n_blocks = sum(1 for o in ops if o["name"].endswith("/c3"))
+    assert n_alias >= n_blocks and all(o["res_grad_fused"] for o in ops if o["kind"] == CONV and o["name"].endswith("/c3"))
+    assert all(o["in_grad_fused"] for o in ops if o["kind"] == UPADD)

@@ -8,6 +8,7 @@ OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
 CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("base", {}),
     ("no_pdl", {"DENSEREG_PDL": "0"}),
+    ("no_grad_alias", {"DENSEREG_GRAD_ALIAS": "0"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
     ("no_lanes_no_pdl", {"DENSEREG_LANES": "0", "DENSEREG_PDL": "0"}),
     ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
