@@ -125,6 +125,8 @@ int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, 
 int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
                      const float* res, int res_cs, float* y, int y_cs, cudaStream_t st);
 // backward reductions: g = dy*(z>0); sums[0:C]=sum g, sums[C:2C]=sum g*xhat   (z = raw*a+b, xhat=(raw-mean)*inv_std)
+int launch_brn_bwd_small(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs, const float* aff, const float* bstat,
+                         const float* beta_gamma, int relu, float* draw, int draw_cs, float* gparam, cudaStream_t st);   // 1 = done in one launch, 0 = not applicable
 int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st);
 // draw = gamma*r*inv_std*(g - sum_g/N - xhat*sum_gx/N); also dbeta,dgamma accumulated into gparam

@@ -887,9 +887,15 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
         if (L.brn) {
           View rv = X.whole(o.raw);
           double* sums = h->sums_bw + L.sum_off;
-          nl += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
-          nl += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
-                                     h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
+          // small layers: reduce + apply by one thread-block cluster in one launch; otherwise two grid-wide passes
+          if (launch_brn_bwd_small(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, h->params + L.p_off, L.relu,
+                                   dz, dz_cs, h->grads + L.p_off, st)) {
+            nl += 1;
+          } else {
+            nl += launch_brn_bwd_reduce(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off, L.relu, sums, st);
+            nl += launch_brn_bwd_apply(np, L.cout, dy, dy_cs, X.ptr(rv), X.cs(rv), h->aff + L.aff_off, h->bstat + L.bstat_off,
+                                       h->params + L.p_off, L.relu, sums, dz, dz_cs, h->grads + L.p_off, st);
+          }
         } else {
           nl += launch_bias_bwd(np, L.cout, dy, dy_cs, X.ptr(o.out), X.cs(o.out), L.relu, o.dropout_tag >= 0, dz, dz_cs, h->grads + L.p_off, st);
         }

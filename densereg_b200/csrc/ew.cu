@@ -438,6 +438,124 @@ __global__ void brn_bwd_apply_v4_kernel(unsigned npix, unsigned C4, const float4
   }
 }
 
+// ---- BRN backward for SMALL layers: reduce + apply in ONE launch by one thread-block cluster --------------------------------------------
+// The <= 8x8 hourglass levels (and everything at a small batch) are a few CTAs' worth of data per layer; with two kernels the layer costs two
+// launch / latency floors on the dependency chain of the backward pass.  Here the 8 CTAs of one cluster each reduce their pixel slice
+// (same channel-stationary float4 mapping as brn_bwd_reduce_v4), publish per-channel partial sums in shared memory, meet at the hardware cluster
+// barrier, add up the 8 partials through distributed shared memory and apply (same arithmetic as brn_bwd_apply_v4) to their own slice, which
+// is still in L1 / L2.  Results are identical to the two-kernel path up to the order of the double-precision partial sums.
+constexpr int BRN_CL = 8;
+DR_DEVINL unsigned brn_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+DR_DEVINL void brn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+DR_DEVINL double brn_ld_remote(const double* local, unsigned rank) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+__global__ void brn_bwd_cluster_kernel(unsigned npix, unsigned C4, const float4* __restrict__ dy, unsigned dy_cs4,
+                                       const float4* __restrict__ raw, unsigned raw_cs4, const float* __restrict__ aff,
+                                       const float* __restrict__ bstat, const float* __restrict__ bg, int relu,
+                                       float4* __restrict__ draw, unsigned draw_cs4, float* __restrict__ gparam) {
+  pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
+  extern __shared__ double red[];                       // [2][blockDim.x][4] block reduction, then part[2][C] (published), tot[2][C]
+  const unsigned lanes = blockDim.x / C4, cq = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const int C = (int)C4 * 4, c = (int)cq * 4;
+  const unsigned rank = brn_cluster_rank();
+  double* part = red + (size_t)blockDim.x * 8;          // [2][C]
+  double* tot = part + 2 * C;                           // [2][C]
+  BrnQuad q; brn_quad_load(q, aff, bstat, C, c);
+  double A[4] = {0.0, 0.0, 0.0, 0.0}, Bs[4] = {0.0, 0.0, 0.0, 0.0};
+  const unsigned stride = BRN_CL * lanes;
+  for (unsigned p0 = rank * lanes + pl; p0 < npix; p0 += 4 * stride) {
+    float4 x4[4], g4[4]; bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned pp = p0 + u * stride; ok[u] = pp < npix;
+      const unsigned pc = ok[u] ? pp : p0;
+      x4[u] = raw[(size_t)pc * raw_cs4 + cq]; g4[u] = dy[(size_t)pc * dy_cs4 + cq];
+    }
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const float xs[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w}, gs[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float g = gs[e];
+        if (relu && !(xs[e] * q.sa[e] + q.sb[e] > 0.f)) g = 0.f;
+        const float xh = (xs[e] - q.mean[e]) * q.istd[e];
+        a[e] += g; b[e] += g * xh;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { A[e] += (double)a[e]; Bs[e] += (double)b[e]; }
+  }
+  double* r0 = red; double* r1 = red + (size_t)blockDim.x * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { r0[threadIdx.x * 4 + e] = A[e]; r1[threadIdx.x * 4 + e] = Bs[e]; }
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double sa = 0.0, sb = 0.0;
+      for (unsigned l = 0; l < lanes; ++l) { sa += r0[(l * C4 + cq) * 4 + e]; sb += r1[(l * C4 + cq) * 4 + e]; }
+      part[c + e] = sa; part[C + c + e] = sb;
+    }
+  }
+  brn_cluster_sync();                                   // every CTA's partials are published
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (unsigned r = 0; r < BRN_CL; ++r) t += brn_ld_remote(part + i, r);
+    tot[i] = t;
+  }
+  brn_cluster_sync();                                   // nobody leaves (or reuses `part`) while a peer may still read it; also orders tot[] for this CTA
+  const double inv_n = 1.0 / (double)npix;
+  {
+    float K[4], mg[4], mgx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      K[e] = __ldg(bg + C + c + e) * __ldg(bstat + 2 * C + c + e) * q.istd[e];
+      mg[e] = (float)(tot[c + e] * inv_n); mgx[e] = (float)(tot[C + c + e] * inv_n);
+    }
+    for (unsigned p0 = rank * lanes + pl; p0 < npix; p0 += 4 * stride) {
+      float4 x4[4], g4[4]; bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned pp = p0 + u * stride; ok[u] = pp < npix;
+        const unsigned pc = ok[u] ? pp : p0;
+        x4[u] = raw[(size_t)pc * raw_cs4 + cq]; g4[u] = dy[(size_t)pc * dy_cs4 + cq];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const float xs[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w}, gs[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float g = gs[e];
+          if (relu && !(xs[e] * q.sa[e] + q.sb[e] > 0.f)) g = 0.f;
+          const float xh = (xs[e] - q.mean[e]) * q.istd[e];
+          o[e] = K[e] * (g - mg[e] - xh * mgx[e]);
+        }
+        draw[(size_t)(p0 + u * stride) * draw_cs4 + cq] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (rank == 0) {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      const float r = bstat[2 * C + cc], d = bstat[3 * C + cc];
+      gparam[cc] += (float)tot[cc];
+      gparam[C + cc] += (float)((double)r * tot[C + cc] + (double)d * tot[cc]);
+    }
+  }
+}
+
 // float4 copy / accumulate of a view (optional depth mask)
 __global__ void copy_view_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ src, unsigned src_cs4, float4* __restrict__ dst,
                                     unsigned dst_cs4, int accumulate, const float* __restrict__ tiny_mask) {
@@ -697,6 +815,30 @@ static bool brn_v4_shape(size_t npix, int C, unsigned* block, unsigned* grid, si
   if (g < 1) g = 1;
   *grid = (unsigned)g;
   return true;
+}
+// one-launch BRN backward for small layers (brn_bwd_cluster_kernel); returns 0 when the layer is too big or not float4-addressable
+int launch_brn_bwd_small(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs, const float* aff, const float* bstat,
+                         const float* beta_gamma, int relu, float* draw, int draw_cs, float* gparam, cudaStream_t st) {
+  static long max_elems = -1;
+  if (max_elems < 0) { const char* e = getenv("DENSEREG_BRN_SMALL_ELEMS"); max_elems = e ? atol(e) : 96 * 1024; }     // npix * C at or below this: one cluster
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const unsigned C4 = (unsigned)C / 4;
+  if (max_elems <= 0 || (long)(npix * (size_t)C) > max_elems || C % 4 != 0 || C4 == 0 || C4 > 128) return 0;
+  if (raw_cs % 4 != 0 || dy_cs % 4 != 0 || draw_cs % 4 != 0 || !al(raw) || !al(dy) || !al(draw)) return 0;
+  const unsigned lanes = 256 / C4, block = C4 * lanes;
+  const size_t smem = ((size_t)block * 8 + 4 * (size_t)C) * sizeof(double);
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(BRN_CL); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = BRN_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = dr_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  if (cudaLaunchKernelEx(&cfg, brn_bwd_cluster_kernel, (unsigned)npix, C4, (const float4*)dy, (unsigned)dy_cs / 4, (const float4*)raw, (unsigned)raw_cs / 4,
+                         aff, bstat, beta_gamma, relu, (float4*)draw, (unsigned)draw_cs / 4, gparam) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return 1;
 }
 int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const float* raw, int raw_cs,
                           const float* aff, const float* bstat, int relu, double* sums, cudaStream_t st) {

@@ -13,6 +13,10 @@ CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("no_lanes_no_pdl", {"DENSEREG_LANES": "0", "DENSEREG_PDL": "0"}),
     ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
     ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
+    ("brn_small_0", {"DENSEREG_BRN_SMALL_ELEMS": "0"}),            # one-cluster BRN backward off / larger reach (default 96 k elements)
+    ("brn_small_48k", {"DENSEREG_BRN_SMALL_ELEMS": "49152"}),
+    ("brn_small_192k", {"DENSEREG_BRN_SMALL_ELEMS": "196608"}),
+    ("brn_small_384k", {"DENSEREG_BRN_SMALL_ELEMS": "393216"}),
 ]
 EXTRA = [a for a in os.environ.get("SWEEP_ARGS", "").split() if a]     # e.g. SWEEP_ARGS="--batch 8 --J 14"
 want = set(sys.argv[1:])
