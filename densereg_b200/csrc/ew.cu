@@ -263,9 +263,10 @@ __global__ void brn_apply_kernel(size_t npix, int C, const float* __restrict__ r
 // float4 variant: C % 4 == 0, all strides % 4 == 0, all bases 16 B aligned; 32-bit index math
 __global__ void brn_apply_v4_kernel(unsigned n4, unsigned C4, const float4* __restrict__ raw, unsigned raw_cs4,
                                     const float4* __restrict__ aff, int relu, const float4* __restrict__ res, unsigned res_cs4,
-                                    float4* __restrict__ y, unsigned y_cs4) {
+                                    float4* __restrict__ y, unsigned y_cs4, int rev) {
   pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += gridDim.x * blockDim.x) {
+    const unsigned i = rev ? n4 - 1 - i0 : i0;      // rev: walk the map from its END (ew_reverse() below)
     const unsigned pix = i / C4, c = i - pix * C4;
     const float4 x = raw[(size_t)pix * raw_cs4 + c], a = __ldg(aff + c), b = __ldg(aff + C4 + c);
     float4 v = make_float4(fmaf(x.x, a.x, b.x), fmaf(x.y, a.y, b.y), fmaf(x.z, a.z, b.z), fmaf(x.w, a.w, b.w));
@@ -342,7 +343,7 @@ DR_DEVINL void brn_quad_load(BrnQuad& q, const float* __restrict__ aff, const fl
 // sums[0:C] += sum g, sums[C:2C] += sum g*xhat  (g = dy * [z > 0]); fp32 partial sums over 4 pixels, then double
 __global__ void brn_bwd_reduce_v4_kernel(unsigned npix, unsigned C4, const float4* __restrict__ dy, unsigned dy_cs4,
                                          const float4* __restrict__ raw, unsigned raw_cs4, const float* __restrict__ aff,
-                                         const float* __restrict__ bstat, int relu, double* __restrict__ sums) {
+                                         const float* __restrict__ bstat, int relu, double* __restrict__ sums, int rev) {
   pdl_trigger(); pdl_wait();      // programmatic dependent launch (common.cuh)
   extern __shared__ double red[];                       // [2][blockDim.x][4]
   const unsigned lanes = blockDim.x / C4, cq = threadIdx.x % C4, pl = threadIdx.x / C4;
@@ -355,7 +356,8 @@ __global__ void brn_bwd_reduce_v4_kernel(unsigned npix, unsigned C4, const float
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const unsigned pp = p0 + u * stride; ok[u] = pp < npix;
-      const unsigned pc = ok[u] ? pp : p0;
+      unsigned pc = ok[u] ? pp : p0;
+      if (rev) pc = npix - 1 - pc;                      // walk the map from its end (ew_reverse())
       x4[u] = raw[(size_t)pc * raw_cs4 + cq]; g4[u] = dy[(size_t)pc * dy_cs4 + cq];
     }
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
@@ -783,6 +785,15 @@ int launch_channel_stats_finalize(size_t npix, int C, const float* x, int x_cs, 
                                                                             update_state);
   return 1;
 }
+// Streaming order.  The conv kernels walk their tiles from the start of a map to its end, so when a conv finishes, the END of its output is what the
+// 126 MB L2 still holds.  The pass that reads that output next (training-mode BRN normalise after the conv; BRN-backward reduce after the dgrad that wrote
+// dy) therefore walks from the end to the start -- it hits L2 for the tail of maps that do not fit (84 MB at 512 channels, batch 40), and leaves the START
+// of its own output in L2 for the next conv.  DENSEREG_EW_REVERSE=0: everything front to back.
+static int ew_reverse() {
+  static int r = -1;
+  if (r < 0) { const char* e = getenv("DENSEREG_EW_REVERSE"); r = (e && e[0] == '0') ? 0 : 1; }
+  return r;
+}
 int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const float* aff, int relu,
                      const float* res, int res_cs, float* y, int y_cs, cudaStream_t st) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -790,7 +801,7 @@ int launch_brn_apply(size_t npix, int C, const float* raw, int raw_cs, const flo
       npix * (size_t)(C / 4) < 0xFFFFFFFFull) {
     const unsigned n4 = (unsigned)(npix * (C / 4));
     dr_launch(brn_apply_v4_kernel, dim3(blocks_for(n4)), dim3(EW_T), 0, st, n4, C / 4, (const float4*)raw, raw_cs / 4, (const float4*)aff, relu,
-                                                        (const float4*)res, res_cs / 4, (float4*)y, y_cs / 4);
+                                                        (const float4*)res, res_cs / 4, (float4*)y, y_cs / 4, ew_reverse());
   } else {
     dr_launch(brn_apply_kernel, dim3(blocks_for(npix * C)), dim3(EW_T), 0, st, npix, C, raw, raw_cs, aff, relu, res, res_cs, y, y_cs);
   }
@@ -846,7 +857,7 @@ int launch_brn_bwd_reduce(size_t npix, int C, const float* dy, int dy_cs, const 
   unsigned block, grid;
   if (raw_cs % 4 == 0 && dy_cs % 4 == 0 && al(raw) && al(dy) && brn_v4_shape(npix, C, &block, &grid, 148)) {
     dr_launch(brn_bwd_reduce_v4_kernel, dim3(grid), dim3(block), (size_t)block * 4 * 2 * sizeof(double), st, (unsigned)npix, (unsigned)C / 4, (const float4*)dy, dy_cs / 4,
-                                                                                        (const float4*)raw, raw_cs / 4, aff, bstat, relu, sums);
+                                                                                        (const float4*)raw, raw_cs / 4, aff, bstat, relu, sums, ew_reverse());
     return 1;
   }
   dr_launch(brn_bwd_reduce_kernel, dim3(stats_grid(npix, C)), dim3(dim3(32, 8)), 0, st, npix, C, dy, dy_cs, raw, raw_cs, aff, bstat, relu, sums);

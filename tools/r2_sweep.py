@@ -13,6 +13,7 @@ CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("no_lanes_no_pdl", {"DENSEREG_LANES": "0", "DENSEREG_PDL": "0"}),
     ("a_tmem_2", {"DENSEREG_TC_A_TMEM": "2"}),
     ("wgrad_streams_1", {"DENSEREG_WGRAD_STREAMS": "1"}),
+    ("ew_reverse_0", {"DENSEREG_EW_REVERSE": "0"}),              # BRN normalise / backward reduce walk front to back like the convs
     ("brn_small_0", {"DENSEREG_BRN_SMALL_ELEMS": "0"}),            # one-cluster BRN backward off / larger reach (default 96 k elements)
     ("brn_small_48k", {"DENSEREG_BRN_SMALL_ELEMS": "49152"}),
     ("brn_small_192k", {"DENSEREG_BRN_SMALL_ELEMS": "196608"}),
