@@ -5,6 +5,8 @@ the default suite covers exactly what ships enabled; tools/r2_sweep.py additiona
   DENSEREG_TC_A_TMEM=0 | 2    A-in-tensor-memory conv kernel nowhere / also instead of CTA pairs  conv_tc_atmem.cu
   DENSEREG_LANES=0            single stream instead of the lane plan                            engine.cu
   DENSEREG_WGRAD_STREAMS=1, DENSEREG_SIDE_STREAM=0   one / no filter-gradient side stream       engine.cu
+  DENSEREG_PDL=0, DENSEREG_GRAD_ALIAS=0   no programmatic dependent launch / residual gradients copied instead of aliased   engine.cu
+  DENSEREG_BRN_SMALL_ELEMS=0, DENSEREG_EW_REVERSE=0   no one-cluster BRN backward / BRN passes front to back               ew.cu
   DENSEREG_WGRAD_SWAP=0, DENSEREG_WGRAD_WAVES=2, DENSEREG_BRN_BLOCKS=1184, DENSEREG_TC_STATS_PER_CTA=0, DENSEREG_POOL_BWD_V4=0   the round-1 settings"""
 import os
 import subprocess
@@ -20,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("env", [{"DENSEREG_WGRAD_A_TMEM": "1"}, {"DENSEREG_TC_A_TMEM": "0"}, {"DENSEREG_TC_A_TMEM": "2"}, 
                                  {"DENSEREG_LANES": "0"}, {"DENSEREG_WGRAD_STREAMS": "1"}, {"DENSEREG_SIDE_STREAM": "0"},
                                  {"DENSEREG_WGRAD_SWAP": "0", "DENSEREG_WGRAD_WAVES": "2", "DENSEREG_BRN_BLOCKS": "1184", "DENSEREG_TC_STATS_PER_CTA": "0",
-                                  "DENSEREG_POOL_BWD_V4": "0"}])
+                                  "DENSEREG_POOL_BWD_V4": "0"},
+                                 {"DENSEREG_PDL": "0"}, {"DENSEREG_GRAD_ALIAS": "0"}, {"DENSEREG_BRN_SMALL_ELEMS": "0", "DENSEREG_EW_REVERSE": "0"}])
 def test_parity_suite_with_switch(env):
     e = dict(os.environ, **env)
     e.pop("DENSEREG_TEST_EXPERIMENTAL", None)
