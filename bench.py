@@ -362,7 +362,7 @@ def run_train(args, c):
     else:
         B = GB
     S, F = 2, 128
-    eng = DenseRegEngine(S, F, J, max_batch=B, precision=args.precision, device=c.local, training=True)
+    eng = DenseRegEngine(S, F, J, max_batch=B, precision=args.precision, device=c.local, training=True, pipeline=args.pipeline)
     eng.torch_sync = torch.cuda.synchronize
     eng.init_params(seed=0)                       # same seed on every rank -> identical replicas without a broadcast
     eng.comm_init(rank, world)                    # in-library NCCL communicator (id broadcast through torch.distributed)
@@ -465,7 +465,8 @@ def run_train(args, c):
             if ref_xyz is not None:
                 mje = joint_error_vs_reference(c, J, args.precision, ref_xyz)
         others = None
-        ws_gb = eng.workspace_bytes / 2**30
+        eng_depth = eng.pipeline_depth
+        ws_gb = eng.workspace_bytes / 2**30 / eng_depth
         if world == 1 and args.config == "icvl_train" and not args.no_other_configs and not args.batch_size and not args.sub_batch:
             eng.close(); del eng; torch.cuda.empty_cache()
             others = other_configs(args)
@@ -475,6 +476,8 @@ def run_train(args, c):
             "dtype": {"fp32": "fp32", "tf32": "tf32", "tf32x3": "fp32 (3xTF32 split, two-level accumulation)"}[args.precision], "data": "synthetic",
             "config": {"workload": desc + ": optimiser step = %d micro-batches x batch %d per GPU, fwd+bwd+allreduce+clip+Adam" % (SUB, B),
                        "name": args.config, "global_batch": B * world, "sub_batch": SUB, "parallelism": "dp%d" % world,
+                       "micro_batch_pipeline": "depth %d%s" % (eng_depth, " (forward of micro-batch i+1 overlaps backward of micro-batch i; forward passes in "
+                                                                "order, one backward at a time, second activation arena)" if eng_depth == 2 else ""),
                        "collective": "1 all-reduce(sum) of the 23.4 MB flat gradient per step inside libdensereg_sm100.so (NCCL, %d bucket call(s) per step "
                                      "overlapped with the last backward pass)" % (n_allreduce // max(args.steps, 1)) if world > 1 else "none (1 GPU)",
                        "l2": "working set ~%.1f GB per micro-batch >> 126 MB L2; inputs rotated over %d batches" % (ws_gb, NROT)},
@@ -491,7 +494,7 @@ def other_configs(args):
     out = {}
     for name, extra in (("msra_infer", ["--steps", "10"]), ("vote", ["--steps", "5"]), ("nyu64_dp", ["--steps", "3"])):
         cmd = [sys.executable, os.path.abspath(__file__), "--config", name, "--no_cpu_baseline", "--no_other_configs", "--precision", args.precision,
-               "--warmup", "3"] + extra
+               "--warmup", "3", "--pipeline", str(args.pipeline)] + extra
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -664,6 +667,7 @@ def main():
     ap.add_argument("--batch_size", type=int, default=0, help="override the config's batch")
     ap.add_argument("--sub_batch", type=int, default=0, help="override the config's micro-batches per optimiser step")
     ap.add_argument("--precision", type=str, default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2], help="training: micro-batch pipeline depth (2 = forward of micro-batch i+1 next to backward of i)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_other_configs", action="store_true", help="default config at N=1 only: do not also measure msra_infer / vote / nyu64_dp in child processes")
     args = ap.parse_args()

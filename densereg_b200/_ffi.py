@@ -60,6 +60,8 @@ SIGNATURES = {
     "dr_vote": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _F, _F, _F, _F, _F, _F, _F, _I32P, _I32P, _P]),
     "dr_infer": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _I32P, _P]),
     "dr_loss_backward": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _F, C.c_uint64, C.c_int, _P]),
+    "dr_pipeline_join": (C.c_int, [_P, _P]),
+    "dr_pipeline_depth": (C.c_int, [_P]),
     "dr_comm_unique_id": (C.c_int, [_P]),
     "dr_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dr_comm_overlap_next_backward": (C.c_int, [_P]),

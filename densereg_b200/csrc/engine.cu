@@ -148,6 +148,20 @@ struct dr_handle {
   bool trace_on = false;
   std::vector<dr_trace_rec> trace;
   float b1p = 1.0f, b2p = 1.0f; int64_t pow_step = 0;      // Adam beta powers (fp32, advanced once per step like TF's variables)
+  // micro-batch pipeline (dr_config.reserved[2] == 2): the sub_batch micro-batches of an optimiser step (train_single_gpu.py:140-148) only
+  // meet in the BRN moving statistics (written by the forward pass) and in the gradient buffer (written by the backward pass), so the
+  // FORWARD pass of micro-batch i+1 may run next to the BACKWARD pass of micro-batch i.  `twin` is a second handle (own activation /
+  // gradient arenas, BRN batch statistics, lanes, filter-gradient streams) bound to the SAME parameter / state / gradient buffers and
+  // sharing this handle's tensor-core weight copies; micro-batches alternate between the two on two internal streams, ordered by events:
+  // forward(i+1) after forward(i) (BRN state order = the reference's), backward(i+1) after backward(i) (exclusive gradient accumulation).
+  dr_handle* twin = nullptr; bool is_twin = false;
+  cudaStream_t pipe_stream[2] = {};
+  cudaEvent_t ev_pipe_in = nullptr, ev_pipe_fwd[2] = {}, ev_pipe_bwd[2] = {}, ev_pipe_loss[2] = {};
+  int pipe_next = 0; bool pipe_pending = false;
+  int64_t pipe_twin_runs = 0;
+  // DENSEREG_CHAIN_PRIO=1: the streams of the dependency chain (pipeline streams, lanes > 0) get the greatest stream priority, so that when SMs
+  // free up the block scheduler serves the chain before the filter-gradient side streams (which only feed the optimiser)
+  int chain_prio = 0;
 };
 
 namespace {
@@ -162,6 +176,8 @@ namespace {
   } while (0)
 
 inline int fail(dr_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+const int kTwinMark = -7777;     // dr_config.reserved[2] of the pipeline's second handle (never creates a twin of its own)
 
 // add the launch count of a run_conv / run_wgrad call, or propagate its (negative) error code
 #define RUN_TRY(acc, expr)                  \
@@ -719,7 +735,7 @@ struct LaneCtx {
 
 int ensure_lanes(dr_handle* h) {
   if (!h->lanes_on || h->ev_pass_start) return DR_OK;
-  for (int l = 1; l < kLanes; ++l) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+  for (int l = 1; l < kLanes; ++l) CUDA_TRY(h, cudaStreamCreateWithPriority(&h->lane_stream[l], cudaStreamNonBlocking, h->chain_prio));
   for (int l = 0; l < kLanes; ++l) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lane_done[l], cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pass_start, cudaEventDisableTiming));
   h->ev_fwd.assign(h->ops.size(), nullptr); h->ev_bwd.assign(h->ops.size(), nullptr);
@@ -832,7 +848,8 @@ int apply_fills(dr_handle* h, Exec& X, const GradWrite& g, cudaStream_t st) {
   return nl;
 }
 
-int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, const float* coms, float* loss_out, cudaStream_t st0) {
+int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, const float* coms, float* loss_out, cudaStream_t st0,
+                  cudaEvent_t ev_after_loss = nullptr) {
   if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
   cudaStream_t st = st0;
   Exec X{h, B, st};
@@ -852,6 +869,7 @@ int backward_impl(dr_handle* h, int B, const float* poses, const float* cfgs, co
   nl += launch_loss(la, st);
   nl += launch_wd(h->n_params, h->params, h->wdmask, h->grads, h->loss_acc + 3, st);
   if (loss_out) nl += launch_finish_loss(h->loss_acc, loss_out, st);
+  if (ev_after_loss) CUDA_TRY(h, cudaEventRecord(ev_after_loss, st));   // pipeline: the caller's inputs (crops, poses, cfgs, coms) are not read after this point
 
   int lane_convs[kLanes] = {};
   int wgrad_count = 0;
@@ -1090,6 +1108,67 @@ int init_device(dr_handle* h) {
   return DR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// micro-batch pipeline (dr_handle::twin)
+// ---------------------------------------------------------------------------------------------
+int pipe_fail(dr_handle* h, dr_handle* e, int rc) { if (e != h) h->err = e->err; return rc; }
+
+// everything the pipeline still has in flight precedes whatever is enqueued on `st` next (gradients complete, arenas idle)
+int pipe_join(dr_handle* h, cudaStream_t st) {
+  if (!h->twin || !h->pipe_pending) return DR_OK;
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_pipe_bwd[k], 0));
+  h->pipe_pending = false; h->pipe_next = 0;
+  return DR_OK;
+}
+
+int pipe_init(dr_handle* h) {
+  if (!h->twin || h->pipe_stream[0]) return DR_OK;
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(h, cudaStreamCreateWithPriority(&h->pipe_stream[k], cudaStreamNonBlocking, h->chain_prio));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_fwd[k], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_bwd[k], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_loss[k], cudaEventDisableTiming));
+  }
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_in, cudaEventDisableTiming));
+  return DR_OK;
+}
+
+// the twin reads this handle's weight copies (built by this handle's forward pass whenever the parameters changed)
+void pipe_share_weights(dr_handle* h) {
+  dr_handle* t = h->twin;
+  t->wk = h->wk; t->wa = h->wa; t->wk_hi = h->wk_hi; t->wk_lo = h->wk_lo; t->wa_hi = h->wa_hi; t->wa_lo = h->wa_lo;
+  t->weights_dirty = false; t->prepped_precision = h->prepped_precision;
+}
+
+int pipe_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses_mm, const float* cfgs, const float* coms, float* loss_out,
+                       uint64_t dropout_seed, int update_state, cudaStream_t caller) {
+  int rc = pipe_init(h);
+  if (rc) return rc;
+  // slot 0 (this handle) whenever the pass has to run here: the weight copies must be rebuilt, the pass all-reduces gradient buckets
+  // through this handle's communicator, or its launches are being timed one by one
+  int k = h->pipe_next;
+  const bool dirty = h->weights_dirty || !h->wk;
+  if (dirty || h->overlap_armed || h->trace_on || trace_env()) k = 0;
+  dr_handle* e = k ? h->twin : h;
+  cudaStream_t es = h->pipe_stream[k];
+  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_in, caller));                  // inputs / zeroed gradients / updated parameters of the caller's stream
+  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_in, 0));
+  if (dirty) CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_bwd[1], 0));  // a twin pass still in flight reads the weight copies about to be rebuilt
+  if (k) { pipe_share_weights(h); ++h->pipe_twin_runs; }
+  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_fwd[k ^ 1], 0));       // BRN moving statistics: forward passes in micro-batch order
+  rc = forward_impl(e, B, dm_mm, coms, 1, update_state, dropout_seed, es);
+  if (rc) return pipe_fail(h, e, rc);
+  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_fwd[k], es));
+  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_bwd[k ^ 1], 0));       // gradient buffer: one backward pass at a time
+  rc = backward_impl(e, B, poses_mm, cfgs, coms, loss_out, es, h->ev_pipe_loss[k]);
+  if (rc) return pipe_fail(h, e, rc);
+  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_bwd[k], es));
+  CUDA_TRY(h, cudaStreamWaitEvent(caller, h->ev_pipe_loss[k], 0));      // loss_out is valid and the inputs are free on the caller's stream
+  h->pipe_next = k ^ 1; h->pipe_pending = true;
+  return DR_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1114,6 +1193,8 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
   { const char* env = getenv("DENSEREG_LANES"); h->lanes_on = !(env && env[0] == '0'); }
   { const char* e = getenv("DENSEREG_TC_CHUNK_EVAL"); if (e) h->chunk_eval = atoi(e) > 0 ? atoi(e) : 0; }
   { const char* e = getenv("DENSEREG_TC_CHUNK_MINKB"); if (e) h->chunk_min_kb = atoi(e) > 0 ? atoi(e) : 0; }
+  { const char* e = getenv("DENSEREG_CHAIN_PRIO");
+    if (e && e[0] == '1') { int lo = 0, hi = 0; if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) h->chain_prio = hi; else cudaGetLastError(); } }
   Builder b{h, 0, 0, 0};
   b.build();
   if (b.plan_overflow) { delete h; return DR_ERR_UNSUPPORTED; }
@@ -1128,12 +1209,34 @@ int dr_create(dr_handle** out, const dr_config* cfg) {
       fprintf(stderr, " rec %d\n", h->plan_bwd[i].record);
     }
   }   // a gradient view with > 4 unwritten channel gaps (never on um_v1)
+  // micro-batch pipeline: a second handle on the same buffers (see dr_handle::twin).  dr_config.reserved[2] == 2 asks for it;
+  // DENSEREG_PIPELINE=2 / =1 forces it on / off for A/B measurements
+  int depth = cfg->reserved[2];
+  { const char* e = getenv("DENSEREG_PIPELINE"); if (e && (e[0] == '1' || e[0] == '2')) depth = e[0] - '0'; }
+  if (depth == 2 && cfg->reserved[2] != kTwinMark) {
+    dr_config c2 = *cfg;
+    c2.reserved[0] = 0; c2.reserved[2] = kTwinMark;
+    if (dr_create(&h->twin, &c2) != DR_OK) { delete h; return DR_ERR_UNSUPPORTED; }
+    h->twin->is_twin = true;
+  }
   *out = h;
   return DR_OK;
 }
 
 int dr_destroy(dr_handle* h) {
   if (!h) return DR_ERR_ARG;
+  if (h->twin) {
+    for (int k = 0; k < 2; ++k) if (h->pipe_stream[k]) cudaStreamSynchronize(h->pipe_stream[k]);
+    dr_destroy(h->twin); h->twin = nullptr;
+    for (int k = 0; k < 2; ++k) {
+      if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
+      if (h->ev_pipe_fwd[k]) cudaEventDestroy(h->ev_pipe_fwd[k]);
+      if (h->ev_pipe_bwd[k]) cudaEventDestroy(h->ev_pipe_bwd[k]);
+      if (h->ev_pipe_loss[k]) cudaEventDestroy(h->ev_pipe_loss[k]);
+    }
+    if (h->ev_pipe_in) cudaEventDestroy(h->ev_pipe_in);
+  }
+  if (h->is_twin) h->wk = h->wa = h->wk_hi = h->wk_lo = h->wa_hi = h->wa_lo = nullptr;     // owned by the first handle
   if (h->nccl_comm) { nccl_api().comm_destroy(h->nccl_comm); h->nccl_comm = nullptr; }
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_bucket_main) cudaEventDestroy(h->ev_bucket_main);
@@ -1166,6 +1269,7 @@ int dr_num_layers(const dr_handle* h) { return h ? (int)h->layers.size() : 0; }
 int dr_debug_get_output(dr_handle* h, int layer, int B, float* dst, int grad, void* stream) {
   if (!h || !dst || layer < 0 || layer >= (int)h->layers.size() || B < 1 || B > h->cap_B) return DR_ERR_ARG;
   if (grad && !h->gact) return fail(h, DR_ERR_STATE, "no gradient workspace");
+  { int rc = pipe_join(h, (cudaStream_t)stream); if (rc) return rc; }     // (pipeline: this handle's arena holds the last micro-batch that ran in slot 0)
   Exec X{h, B, (cudaStream_t)stream};
   for (const Op& o : h->ops) {
     if (o.kind == OP_CONV && o.layer == layer) {
@@ -1211,9 +1315,9 @@ int dr_debug_op(const dr_handle* h, int idx, dr_op_info* out) {
   return DR_OK;
 }
 
-int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches : 0; }
-int64_t dr_tc_launch_count(const dr_handle* h) { return h ? h->tc_launches : 0; }
-size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes : 0; }
+int64_t dr_launch_count(const dr_handle* h) { return h ? h->launches + (h->twin ? h->twin->launches : 0) : 0; }
+int64_t dr_tc_launch_count(const dr_handle* h) { return h ? h->tc_launches + (h->twin ? h->twin->tc_launches : 0) : 0; }
+size_t dr_workspace_bytes(const dr_handle* h) { return h ? h->ws_bytes + (h->twin ? h->twin->ws_bytes : 0) : 0; }
 
 int dr_get_layer(const dr_handle* h, int idx, dr_layer_info* out) {
   if (!h || !out || idx < 0 || idx >= (int)h->layers.size()) return DR_ERR_ARG;
@@ -1230,7 +1334,11 @@ int dr_bind(dr_handle* h, float* params, float* state, float* grads, float* adam
   if (!h || !params || !state) return DR_ERR_ARG;
   h->params = params; h->state = state; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
   h->weights_dirty = true;
-  return init_device(h);
+  int rc = init_device(h);
+  if (rc || !h->twin) return rc;
+  rc = dr_bind(h->twin, params, state, grads, adam_m, adam_v);      // same buffers: the two arenas of the micro-batch pipeline
+  if (rc) h->err = h->twin->err;
+  return rc;
 }
 
 int dr_params_changed(dr_handle* h) {
@@ -1243,6 +1351,7 @@ int dr_init_params(dr_handle* h, uint64_t seed, float stddev, void* stream) {
   if (!h) return DR_ERR_ARG;
   if (!h->params || !h->state) return fail(h, DR_ERR_STATE, "dr_bind() not called");
   cudaStream_t st = (cudaStream_t)stream;
+  { int rc = pipe_join(h, st); if (rc) return rc; }
   h->launches += launch_init_trunc_normal(h->n_params, h->params, stddev, seed, st);
   init_state_kernel<<<(unsigned)h->layers.size(), 128, 0, st>>>(h->ltab, h->params, h->state); ++h->launches;
   h->weights_dirty = true;
@@ -1272,7 +1381,9 @@ int dr_forward(dr_handle* h, int B, const float* dm_mm, const float* coms,
                int is_training, int update_state, uint64_t dropout_seed, void* stream) {
   if (!h || !dm_mm || !coms) return DR_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = forward_impl(h, B, dm_mm, coms, is_training, update_state, dropout_seed, st);
+  int rc = pipe_join(h, st);
+  if (rc) return rc;
+  rc = forward_impl(h, B, dm_mm, coms, is_training, update_state, dropout_seed, st);
   if (rc) return rc;
   copy_outputs(h, B, hm, hm3, um, st);
   CUDA_TRY(h, cudaGetLastError());
@@ -1308,6 +1419,7 @@ int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, const f
              float* xyz_mm, int32_t* top5_idx, void* stream) {
   if (!h || !dm_mm || !cfgs || !coms || !xyz_mm) return DR_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  { int rc = pipe_join(h, st); if (rc) return rc; }
   if (h->cfg.reserved[0] == 0) {                          // eager
     int rc = infer_enqueue(h, B, dm_mm, cfgs, coms, xyz_mm, top5_idx, st);
     if (rc) return rc;
@@ -1359,10 +1471,18 @@ int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses
   if (!h || !dm_mm || !poses_mm || !cfgs || !coms) return DR_ERR_ARG;
   if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->twin) return pipe_loss_backward(h, B, dm_mm, poses_mm, cfgs, coms, loss_out, dropout_seed, update_state, st);
   int rc = forward_impl(h, B, dm_mm, coms, 1, update_state, dropout_seed, st);
   if (rc) return rc;
   return backward_impl(h, B, poses_mm, cfgs, coms, loss_out, st);
 }
+
+int dr_pipeline_join(dr_handle* h, void* stream) {
+  if (!h) return DR_ERR_ARG;
+  return pipe_join(h, (cudaStream_t)stream);
+}
+
+int dr_pipeline_depth(const dr_handle* h) { return h ? (h->twin ? 2 : 1) : 0; }
 
 int dr_comm_unique_id(void* out128) {
   if (!out128) return DR_ERR_ARG;
@@ -1405,6 +1525,7 @@ int64_t dr_comm_allreduce_count(const dr_handle* h) { return h ? h->allreduce_ca
 int dr_zero_grads(dr_handle* h, void* stream) {
   if (!h) return DR_ERR_ARG;
   if (!h->grads) return fail(h, DR_ERR_STATE, "grads buffer not bound");
+  { int rc = pipe_join(h, (cudaStream_t)stream); if (rc) return rc; }
   CUDA_TRY(h, cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(float), (cudaStream_t)stream));
   return DR_OK;
 }
@@ -1413,6 +1534,7 @@ int dr_optimizer_step(dr_handle* h, int accum_steps, int world, float lr, int64_
   if (!h || accum_steps < 1 || world < 1 || step < 1) return DR_ERR_ARG;
   if (!h->grads || !h->adam_m || !h->adam_v || !h->params) return fail(h, DR_ERR_STATE, "grads / adam buffers not bound");
   cudaStream_t ost = (cudaStream_t)stream;
+  { int rc = pipe_join(h, ost); if (rc) return rc; }
   if (h->nccl_comm && h->comm_world > 1) {
     if (world != h->comm_world) return fail(h, DR_ERR_ARG, "dr_optimizer_step: world differs from the communicator's size");
     if (!h->reduced_in_backward) {                          // not overlapped with the last backward: one all-reduce of the whole buffer now
@@ -1480,6 +1602,7 @@ int dr_debug_conv(dr_handle* h, int layer, int B, const float* x, float* y, int 
   precision &= 0xff;
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !y || B < 1) return DR_ERR_ARG;
   if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
+  { int rc = pipe_join(h, (cudaStream_t)stream); if (rc) return rc; }
   const Layer& L = h->layers[layer];
   ConvProblem p; memset(&p, 0, sizeof(p));
   p.x = x; p.x_cs = L.cin; p.B = B; p.H = L.in_hw; p.W = L.in_hw; p.Cin = L.cin; p.Ho = L.out_hw; p.Wo = L.out_hw; p.Cout = L.cout;
@@ -1496,6 +1619,7 @@ int dr_debug_conv_bwd(dr_handle* h, int layer, int B, const float* x, const floa
   if (!h || layer < 0 || layer >= (int)h->layers.size() || !x || !dy || B < 1) return DR_ERR_ARG;
   if (!h->params) return fail(h, DR_ERR_STATE, "dr_bind() not called");
   cudaStream_t st = (cudaStream_t)stream;
+  { int rc = pipe_join(h, st); if (rc) return rc; }
   const Layer& L = h->layers[layer];
   const size_t nw = (size_t)L.k * L.k * L.cin * L.cout;
   if (dw) {

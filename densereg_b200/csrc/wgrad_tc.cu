@@ -37,6 +37,8 @@ struct WgParams {
   float* dw;
   int n_tiles, splits;   // persistent kernel: work item = (split, tap, m tile, n tile), n fastest
   int swap;              // 1: roles exchanged -- M = cout tile (A = dY, unshifted), N = cin tile (B = X at the tap's offset); see launch_wgrad_tc
+  int trunc_hi;          // 3xTF32: 1 = the landed fp32 tile IS the hi operand (the tensor core ignores the low 13 mantissa bits of a kind::tf32
+                         // operand = truncation), the splitters only write lo = rn_tf32(v - trunc(v)): half the splitter's shared-memory writes
 };
 
 template <bool SPLIT3>
@@ -177,13 +179,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_wait(&full_bar[s], ph);
       float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + WG_A_BYTES + b_bytes);
-      for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
-        float4 a = hi[idx], h, l;
-        h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
-        h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
-        h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
-        h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
-        hi[idx] = h; lo[idx] = l;
+      if (p.trunc_hi) {
+        for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
+          const float4 a = hi[idx];
+          float4 l;
+          l.x = tf32_rna(a.x - tf32_trunc(a.x)); l.y = tf32_rna(a.y - tf32_trunc(a.y));
+          l.z = tf32_rna(a.z - tf32_trunc(a.z)); l.w = tf32_rna(a.w - tf32_trunc(a.w));
+          lo[idx] = l;
+        }
+      } else {
+        for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
+          float4 a = hi[idx], h, l;
+          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
+          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
+          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
+          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
+          hi[idx] = h; lo[idx] = l;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -476,6 +488,9 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   t.kb_per_split = (t.total_kb + splits - 1) / splits;
   splits = (t.total_kb + t.kb_per_split - 1) / t.kb_per_split;
   t.n_tiles = cout_tiles; t.splits = splits;
+  static int trunc_hi = -1;
+  if (trunc_hi < 0) { const char* e = getenv("DENSEREG_SPLIT_TRUNC"); trunc_hi = e ? (atoi(e) & 1) : 0; }
+  t.trunc_hi = trunc_hi;
   int cols = 32; while (cols < BN) cols <<= 1;
   t.tmem_cols = cols;
   const int stage_bytes = (split3 ? 2 : 1) * (WG_A_BYTES + t.nchunks_b * WG_CHUNK_BYTES);

@@ -24,7 +24,7 @@ def _ptr(t):
 
 class DenseRegEngine:
     def __init__(self, num_stack=2, num_fea=128, num_jnt=16, max_batch=40, precision="tf32x3", device=0,
-                 kernel_size=3, training=True, infer_graph=False, tc_pair=True):
+                 kernel_size=3, training=True, infer_graph=False, tc_pair=True, pipeline=1):
         if not torch.cuda.is_available():
             raise DenseRegError("densereg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _ffi.load()
@@ -37,6 +37,7 @@ class DenseRegEngine:
                             device=device)
         cfg.reserved[0] = 1 if infer_graph else 0          # dr_infer via a captured CUDA graph (same buffers every call)
         cfg.reserved[1] = 0 if tc_pair else -1             # CTA-pair (cta_group::2) 3xTF32 conv kernel for the big layers (default on)
+        cfg.reserved[2] = 2 if (pipeline == 2 and training) else 0   # micro-batch pipeline: forward of micro-batch i+1 next to backward of i (join())
         self._h = C.c_void_p()
         torch.cuda.set_device(self.device)
         rc = self.lib.dr_create(C.byref(self._h), C.byref(cfg))
@@ -205,6 +206,15 @@ class DenseRegEngine:
     @property
     def allreduce_count(self):
         return int(self.lib.dr_comm_allreduce_count(self._h))
+
+    def join(self):
+        """Micro-batch pipeline (pipeline=2): order the current stream after every backward pass still in flight.  Needed only before
+        reading `self.grads` directly; zero_grads / optimizer_step / forward / infer join by themselves."""
+        self._check(self.lib.dr_pipeline_join(self._h, self._stream()))
+
+    @property
+    def pipeline_depth(self):
+        return int(self.lib.dr_pipeline_depth(self._h))
 
     def zero_grads(self):
         self._check(self.lib.dr_zero_grads(self._h, self._stream()))

@@ -48,6 +48,8 @@ def build_argparser():
     p.add_argument("--kernel_size", type=int, default=3)
     # additions (not in the reference): arithmetic mode and a bound on synthetic steps
     p.add_argument("--precision", type=str, default="tf32x3", choices=["fp32", "tf32", "tf32x3"])
+    p.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                   help="2 = micro-batch pipeline: the forward pass of micro-batch i+1 runs next to the backward pass of micro-batch i (second activation arena)")
     p.add_argument("--max_steps", type=int, default=0, help="stop after this many optimiser steps (0 = epoch schedule)")
     p.add_argument("--test_num", type=int, default=0, help="number of synthetic test frames (0 = dataset's exact_num)")
     p.add_argument("--restore_step", type=int, default=None,
@@ -181,7 +183,7 @@ class JointDetectionModel:
         self.world = world
         self.engine = DenseRegEngine(flags.num_stack, flags.num_fea, self._jnt_num, max_batch=flags.batch_size,
                                      precision=flags.precision, device=device, kernel_size=flags.kernel_size,
-                                     training=bool(flags.is_train))
+                                     training=bool(flags.is_train), pipeline=getattr(flags, "pipeline", 1))
 
     # ---- trainer/tester contract -----------------------------------------------------
     @property
@@ -300,6 +302,8 @@ def train(model, rank=0, world=1, log=print, start_step=0):
             ave_loss = loss.clone() if ave_loss is None else ave_loss + loss           # ave_loss += loss_value :147 (device add, no sync)
             nf = ~torch.isfinite(loss[0])
             bad = nf if bad is None else (bad | nf)
+        if world > 1:
+            eng.join()                                                             # micro-batch pipeline: every backward pass has written its gradients
         allreduce_gradients(eng.grads, world)
         eng.optimizer_step(step + 1, model.lr_at(step), accum_steps=f.sub_batch, world=world)   # train_op :150
         if step % 5 == 0 or step + 1 == max_steps:                                 # every rank checks its own micro-batches (:146), one sync per 5 steps

@@ -57,7 +57,8 @@ typedef struct {
   int32_t precision;     /* dr_precision                 */
   int32_t device;        /* CUDA ordinal                 */
   int32_t reserved[7];   /* reserved[0] != 0: dr_infer replays a CUDA graph captured per (batch, pointer) key;
-                            reserved[1] < 0: do NOT run the 3xTF32 convs of the big layers on CTA pairs (tcgen05 cta_group::2; default on) */
+                            reserved[1] < 0: do NOT run the 3xTF32 convs of the big layers on CTA pairs (tcgen05 cta_group::2; default on);
+                            reserved[2] == 2: micro-batch pipeline for training (see dr_pipeline_join) */
 } dr_config;
 
 typedef struct dr_handle dr_handle;
@@ -133,6 +134,18 @@ DR_API int dr_infer(dr_handle* h, int B, const float* dm_mm, const float* cfgs, 
 DR_API int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* poses_mm,
                      const float* cfgs, const float* coms, float* loss_out,
                      uint64_t dropout_seed, int update_state, void* stream);
+
+/* Micro-batch pipeline (dr_config.reserved[2] == 2; doubles the activation workspace).  The sub_batch micro-batches of one optimiser
+ * step (model/train_single_gpu.py:140-148: `for sub in range(sub_batch): sess.run([loss, accum_op])`) only meet in the BRN moving
+ * statistics (written by the forward pass, network/slim/ops.py:141-162) and in the gradient accumulators (written by the backward pass,
+ * train_single_gpu.py:69-84).  With the pipeline on, consecutive dr_loss_backward calls alternate between two activation arenas on two
+ * internal streams: the FORWARD pass of micro-batch i+1 runs next to the BACKWARD pass of micro-batch i; forward passes stay in call order
+ * (same BRN state sequence as the reference), backward passes never overlap each other.  On return the caller's stream is ordered after
+ * the forward pass and the loss of THIS micro-batch (loss_out valid, inputs reusable) but not after its backward pass: dr_zero_grads,
+ * dr_optimizer_step, dr_forward, dr_infer and the debug entry points join the pipeline themselves; a caller that reads the bound grads
+ * buffer directly calls dr_pipeline_join(h, stream) first.  dr_pipeline_depth: 1 (off) or 2. */
+DR_API int dr_pipeline_join(dr_handle* h, void* stream);
+DR_API int dr_pipeline_depth(const dr_handle* h);
 
 /* Data-parallel communicator: replaces model/train_multi_gpu.py:16-39 (_average_gradients: per-variable concat + mean through host
  * memory) and :63-64,73-92 (towers) with one process per GPU and ONE NCCL all-reduce(sum) of the flat gradient per optimiser step.

@@ -36,6 +36,7 @@ class FakeEngine:
         self.params.copy_(params)
         if state is not None: self.state.copy_(state)
     def zero_grads(self): self.grads.zero_(); self.calls.append(("zero",))
+    def join(self): self.calls.append(("join",))
     def loss_backward(self, dms, poses, cfgs, coms, dropout_seed=0, update_state=True):
         assert dms.shape[1:] == (128, 128, 1) and poses.shape[1] == 3 * self.J and cfgs.shape[1] == 6 and coms.shape[1] == 3
         self.grads += 1.0; self.calls.append(("loss", dms.shape[0], dropout_seed))

@@ -7,6 +7,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
 CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("base", {}),
+    ("pipe2", {"DENSEREG_PIPELINE": "2"}),                         # micro-batch pipeline: forward(i+1) next to backward(i)
+    ("pipe2_prio", {"DENSEREG_PIPELINE": "2", "DENSEREG_CHAIN_PRIO": "1"}),
+    ("pipe2_wgrad_a_tmem", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_A_TMEM": "1"}),
+    ("pipe2_no_lanes", {"DENSEREG_PIPELINE": "2", "DENSEREG_LANES": "0"}),
+    ("pipe2_wgrad_streams_1", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_STREAMS": "1"}),
+    ("chain_prio", {"DENSEREG_CHAIN_PRIO": "1"}),
+    ("pipe2_trunc", {"DENSEREG_PIPELINE": "2", "DENSEREG_SPLIT_TRUNC": "1"}),       # wgrad: landed fp32 tile = hi operand, splitters write lo only
+    ("trunc", {"DENSEREG_SPLIT_TRUNC": "1"}),
+    ("pipe2_trunc_waves2", {"DENSEREG_PIPELINE": "2", "DENSEREG_SPLIT_TRUNC": "1", "DENSEREG_WGRAD_WAVES": "2"}),
+    ("pipe2_waves2", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_WAVES": "2"}),
     ("no_pdl", {"DENSEREG_PDL": "0"}),
     ("no_grad_alias", {"DENSEREG_GRAD_ALIAS": "0"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
