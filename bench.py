@@ -383,9 +383,14 @@ def run_train(args, c):
         eng.optimizer_step(i + 1, 1e-3, accum_steps=SUB, world=world)
 
     def step_e2e(i):
+        # inputs are copied ONE micro-batch ahead (the usual loader prefetch): after a pipelined dr_loss_backward the caller's stream is
+        # ordered behind that micro-batch's forward pass, so a copy issued after the call would start that late
         eng.zero_grads()
+        nxt = [t.to(dev, non_blocking=True) for t in pinned[(i * SUB) % NROT]]
         for sub in range(SUB):
-            d, po, cf, co = [t.to(dev, non_blocking=True) for t in pinned[(i * SUB + sub) % NROT]]
+            d, po, cf, co = nxt
+            if sub + 1 < SUB:
+                nxt = [t.to(dev, non_blocking=True) for t in pinned[(i * SUB + sub + 1) % NROT]]
             if sub == SUB - 1:
                 eng.comm_overlap_next_backward()
             loss = eng.loss_backward(d, po, cf, co, dropout_seed=i * SUB + sub)

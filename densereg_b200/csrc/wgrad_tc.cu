@@ -11,8 +11,11 @@
 //   B = dY  : BN/32 boxes of d(raw conv output), unshifted, same layout.
 //   4 MMAs (M=128, N=BN, K=8 pixels, kind::tf32, a_major = b_major = MN) per k-block; UMMA descriptors: LBO = 4096 B between
 //   32-wide chunks, SBO = 512 B between 4-pixel groups, start advanced by 1024 B per K=8 step.
-//   3xTF32 (DR_PREC_TF32X3): eight splitter warps rewrite each landed stage in place into hi = rn_tf32(v) and lo = rn_tf32(v-hi)
-//   (A and B), 3 MMAs per k-step.
+//   3xTF32 (DR_PREC_TF32X3): 3 MMAs per k-step (hi*lo, lo*hi, hi*hi).  The tensor core reads sign, exponent and the top 10 mantissa bits of a
+//   32-bit kind::tf32 operand, i.e. it TRUNCATES: the landed fp32 stage itself is the hi operand, and the eight splitter warps only write
+//   lo = rn_tf32(v - trunc(v)) (exact difference, |lo| < 2^-10 |v|, representation error <= 2^-21 |v|, unbiased) next to it -- half the
+//   shared-memory writes of a split that also rewrites hi (DENSEREG_SPLIT_TRUNC=0 restores hi = rn_tf32(v), lo = rn_tf32(v - hi) in place).
+//   What the 3-product scheme drops is lo*lo <= 2^-20 |a b| with the sign of a*b (2^-22 on average: a uniform relative shrink of 2.4e-7).
 // Epilogue: tcgen05.ld -> red.global.add.f32 into the flat gradient (split over pixel ranges across blockIdx.z, and micro-batch
 // accumulation, are both just "+=").
 #include "tc_common.cuh"
@@ -444,6 +447,212 @@ wgrad_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 }
 
+// ---- CTA-pair (cta_group::2) 3xTF32 variant for the wide layers (M = max(cin, cout) >= 256) ---------------------------------------------
+// Why: with both operands split in shared memory a one-CTA 128 x 128 tile moves 192 KB of shared-memory traffic per 32-pixel k-block
+// (32 KB TMA, 32 KB read + 32 KB written by the splitters, 12 MMAs x 8 KB operand reads) against 768 MMA cycles = 250 B/clk asked of a
+// 128 B/clk shared memory (ncu: tensor pipe 40 % active on um_comb/c2).  A CTA pair computes D[256 rows, BN <= 256 columns] with ONE
+// tcgen05.mma.cta_group::2 per k-step: each SM supplies its own 128-row A tile and only HALF of the B tile, and holds 128 x BN of the
+// accumulator -- at BN = 256 the same 192 KB per k-block now feed 1536 MMA cycles (125 B/clk).
+// Protocol = conv_tc_pair.cu (rank 0 = leader): both CTAs run producer / splitters / epilogue on their own shared memory and tensor
+// memory lanes; the splitters of both CTAs arrive on the LEADER's split[s]; the leader's single MMA thread issues the 12 MMAs per
+// k-block and frees stage s in both CTAs with a multicast commit; after the last k-block a multicast commit releases both epilogues.
+// Splitters always use the truncation form (the landed fp32 tile is the hi operand, only lo is written): stage = [A | Bh | A_lo | Bh_lo].
+DR_DEVINL uint32_t wg_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DR_DEVINL void wg_cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+DR_DEVINL uint32_t wg_mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+DR_DEVINL void wg_mbar_arrive_cluster(uint32_t cluster_addr) {      // default (CTA-scope) semantics: see conv_tc_pair.cu
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+DR_DEVINL void wg_commit_pair(uint64_t* bar) {                      // arrives on `bar` at the same offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+DR_DEVINL void wg_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// grid (2 * taps * m_pairs, n_tiles, splits), cluster (2,1,1); p.cin_tiles = number of 256-row M pairs, p.nchunks_b = 32-wide chunks of HALF a B tile
+__global__ void __launch_bounds__(192 + WG_SPLIT_THREADS, 1)
+wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgParams p) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int bh_bytes = p.nchunks_b * WG_CHUNK_BYTES;                  // this CTA's half of the B tile
+  const int half_bytes = WG_A_BYTES + bh_bytes;                       // [A | Bh] as landed (= the hi operands)
+  const int stage_bytes = 2 * half_bytes;                             // + [A_lo | Bh_lo]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);   // local: TMA landed
+  uint64_t* empty_bar = full_bar + p.stages;                          // local: slot free (multicast commit of the leader)
+  uint64_t* split_bar = empty_bar + p.stages;                         // LEADER's copy is used: both CTAs' stages split
+  uint64_t* accum_bar = split_bar + p.stages;                         // local: accumulator complete (multicast commit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = wg_cluster_ctarank();
+  const int pair_idx = blockIdx.x >> 1;
+  const int tap = pair_idx / p.cin_tiles;
+  const int c0 = (pair_idx - tap * p.cin_tiles) * 256 + (int)rank * 128;   // first M row of THIS CTA: cin (cout when swapped)
+  const int n_tile0 = blockIdx.y * p.BN;                                    // first N column of the pair's tile
+  const int n0 = n_tile0 + (int)rank * (p.BN / 2);                          // first N column this CTA LOADS (its half of B)
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.total_kb) kb_end = p.total_kb;
+  const int num_kb = kb_end - kb_begin;           // >= 1 by construction, identical in both CTAs
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 2 * (WG_SPLIT_THREADS / 32)); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {      // one warp of EACH CTA (same warp id) allocates with cta_group::2
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  wg_cluster_sync_all();           // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dy = tap / p.ksz - p.pad, dx = tap % p.ksz - p.pad;
+      const uint32_t tx = (uint32_t)half_bytes;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int pix = (kb_begin + i) * WG_KB;
+        const int img = pix / (p.H * p.W);
+        const int rem = pix - img * p.H * p.W;
+        const int y = rem / p.W, x = rem - y * p.W;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx);
+        if (!p.swap) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(&map_x, &full_bar[s], st + j * WG_CHUNK_BYTES, c0 + 32 * j, x + dx, y + dy, img);
+          for (int j = 0; j < p.nchunks_b; ++j)
+            tma_load_4d(&map_dy, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, n0 + 32 * j, x, y, img);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(&map_dy, &full_bar[s], st + j * WG_CHUNK_BYTES, c0 + 32 * j, x, y, img);
+          for (int j = 0; j < p.nchunks_b; ++j)
+            tma_load_4d(&map_x, &full_bar[s], st + WG_A_BYTES + j * WG_CHUNK_BYTES, n0 + 32 * j, x + dx, y + dy, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      // a_format = b_format = TF32, c = F32, a_major = b_major = MN (bits 15, 16), N = BN, M = 256 (both CTAs)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+        mbar_wait(&split_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + WG_A_BYTES;
+        const uint32_t lo_off = (uint32_t)half_bytes;
+#pragma unroll
+        for (int k = 0; k < WG_KB / 8; ++k) {
+          const uint64_t ad = make_desc_mn(a_addr + k * 1024, WG_CHUNK_BYTES, 512);
+          const uint64_t bd = make_desc_mn(b_addr + k * 1024, WG_CHUNK_BYTES, 512);
+          const uint64_t ald = make_desc_mn(a_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
+          const uint64_t bld = make_desc_mn(b_addr + lo_off + k * 1024, WG_CHUNK_BYTES, 512);
+          wg_mma_tf32_pair(tmem_base, ad, bld, idesc, (i | k) != 0);
+          wg_mma_tf32_pair(tmem_base, ald, bd, idesc, 1);
+          wg_mma_tf32_pair(tmem_base, ad, bd, idesc, 1);
+        }
+        wg_commit_pair(&empty_bar[s]);           // frees the stage in both CTAs when these MMAs retire
+      }
+      wg_commit_pair(accum_bar);                 // accumulator complete -> both epilogues
+    }
+  } else if (warp < 6) {
+    mbar_wait_sleep(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int c = c0 + q * 32 + lane;                       // TMEM lane == M row of this CTA's half of the tile
+    if (!p.swap) {
+      const bool cvalid = c < p.Cin;
+      float* row = p.dw + ((size_t)tap * p.Cin + c) * p.Cout;
+      for (int cb = 0; cb < p.BN; cb += 32) {
+        if (n_tile0 + cb >= p.Cout) break;                  // warp-uniform: nothing but padding from here on
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+        if (!cvalid) continue;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n_tile0 + cb + e;
+          if (n < p.Cout) atomicAdd(row + n, __uint_as_float(v[e]));
+        }
+      }
+    } else {
+      const bool cvalid = c < p.Cout;
+      float* col = p.dw + (size_t)tap * p.Cin * p.Cout + c;
+      for (int cb = 0; cb < p.BN; cb += 32) {
+        if (n_tile0 + cb >= p.Cin) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+        if (!cvalid) continue;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n_tile0 + cb + e;
+          if (n < p.Cin) atomicAdd(col + (size_t)n * p.Cout, __uint_as_float(v[e]));
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    const int t = threadIdx.x - 192;
+    const int n16 = half_bytes / 16;                          // float4 elements of [A | Bh]
+    const uint32_t split_leader = wg_mapa_u32(smem_u32(&split_bar[0]), 0);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % p.stages;
+      const uint32_t ph = (uint32_t)(i / p.stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + half_bytes);
+      for (int idx = t; idx < n16; idx += WG_SPLIT_THREADS) {
+        const float4 a = hi[idx];
+        float4 l;
+        l.x = tf32_rna(a.x - tf32_trunc(a.x)); l.y = tf32_rna(a.y - tf32_trunc(a.y));
+        l.z = tf32_rna(a.z - tf32_trunc(a.z)); l.w = tf32_rna(a.w - tf32_trunc(a.w));
+        lo[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) wg_mbar_arrive_cluster(split_leader + (uint32_t)s * 8u);
+    }
+  }
+
+  // the peer's shared memory and barriers must stay alive until the leader's last MMA / multicast commit has retired
+  tc_fence_before();
+  __syncthreads();
+  wg_cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 bool wgrad_tc_eligible(const WgradProblem& p) {
@@ -489,7 +698,7 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   splits = (t.total_kb + t.kb_per_split - 1) / t.kb_per_split;
   t.n_tiles = cout_tiles; t.splits = splits;
   static int trunc_hi = -1;
-  if (trunc_hi < 0) { const char* e = getenv("DENSEREG_SPLIT_TRUNC"); trunc_hi = e ? (atoi(e) & 1) : 0; }
+  if (trunc_hi < 0) { const char* e = getenv("DENSEREG_SPLIT_TRUNC"); trunc_hi = e ? (atoi(e) & 1) : 1; }   // default since round 2: wgrad 5.54 -> 4.99 ms per micro-batch, dW error 4e-6 .. 8e-6 (bar 2e-5)
   t.trunc_hi = trunc_hi;
   int cols = 32; while (cols < BN) cols <<= 1;
   t.tmem_cols = cols;
@@ -512,6 +721,47 @@ int launch_wgrad_tc(const WgradProblem& p, int split3, cudaStream_t st) {
   cuuint64_t yd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
   cuuint64_t ys[3] = {(cuuint64_t)p.dy_cs * 4, (cuuint64_t)p.W * p.dy_cs * 4, (cuuint64_t)p.H * p.W * p.dy_cs * 4};
   if (!encode_map(&mdy, p.dy, 4, yd, ys, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 0;
+
+  // CTA pairs for the wide layers (kernel comment above): M = max side >= 256 (DENSEREG_WGRAD_PAIR_MINM; 0 = off), 3xTF32 only
+  static int pair_min_m = -1;
+  if (pair_min_m < 0) { const char* e = getenv("DENSEREG_WGRAD_PAIR_MINM"); pair_min_m = e ? atoi(e) : 256; }
+  if (split3 && pair_min_m > 0 && Mdim >= pair_min_m && Mdim > 128) {
+    WgParams tp = t;
+    int PBN = (Ndim + 63) / 64 * 64;                        // each CTA loads half of the tile in whole 32-channel chunks
+    if (PBN > 256) PBN = 256;
+    tp.BN = PBN; tp.nchunks_b = PBN / 64;
+    tp.cin_tiles = (Mdim + 255) / 256;                      // 256-row M pairs
+    const int n_tiles = (Ndim + PBN - 1) / PBN;
+    const int ptiles = tp.cin_tiles * p.k * p.k * n_tiles;
+    int psplits = (waves * 74) / ptiles;                    // one wave of CTA pairs
+    if (psplits > tp.total_kb / 8) psplits = tp.total_kb / 8;
+    if (psplits < 1) psplits = 1;
+    tp.kb_per_split = (tp.total_kb + psplits - 1) / psplits;
+    psplits = (tp.total_kb + tp.kb_per_split - 1) / tp.kb_per_split;
+    tp.n_tiles = n_tiles; tp.splits = psplits; tp.trunc_hi = 1;
+    int pcols = 32; while (pcols < PBN) pcols <<= 1;
+    tp.tmem_cols = pcols;
+    const int pstage = 2 * (WG_A_BYTES + tp.nchunks_b * WG_CHUNK_BYTES);
+    int pstages = (208 * 1024) / pstage;
+    if (pstages > 6) pstages = 6;
+    tp.stages = pstages;
+    const size_t psmem = (size_t)pstages * pstage + (3 * pstages + 1) * 8 + 16 + 1024 + 64;
+    static bool pattr = false;
+    if (!pattr) {
+      if (!launch_ok(cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024), "wgrad_tc_pair_kernel smem attribute")) return 0;
+      pattr = true;
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * tp.cin_tiles * p.k * p.k, n_tiles, psplits); cfg.blockDim = dim3(192 + WG_SPLIT_THREADS);
+    cfg.dynamicSmemBytes = psmem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = dr_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    return launch_ok(cudaLaunchKernelEx(&cfg, wgrad_tc_pair_kernel, mx, mdy, tp), "wgrad_tc_pair_kernel") ? 1 : 0;
+  }
 
   static int atmem = -1;
   if (atmem < 0) { const char* e = getenv("DENSEREG_WGRAD_A_TMEM"); atmem = (e && e[0] == '1') ? 1 : 0; }

@@ -294,10 +294,16 @@ def train(model, rank=0, world=1, log=print, start_step=0):
         t_step = time.time()
         eng.zero_grads()                                                           # reset_op :139
         ave_loss = None
+        def fetch(sub):                                                            # one micro-batch of device inputs (+ augmentation, hourglass_um_crop_tiny.py:333-334)
+            t = list(model.train_dataset.batch_device(eng, f.batch_size, seed=step * f.sub_batch + sub, lo=lo, hi=hi)[:4])
+            if f.is_aug:
+                t[0], t[1] = augment(eng, t, rng)
+            return t
+        nxt = fetch(0)
         for sub in range(f.sub_batch):                                             # :140-148
-            tens = list(model.train_dataset.batch_device(eng, f.batch_size, seed=step * f.sub_batch + sub, lo=lo, hi=hi)[:4])
-            if f.is_aug:                                                               # hourglass_um_crop_tiny.py:333-334
-                tens[0], tens[1] = augment(eng, tens, rng)
+            tens = nxt                                                                 # inputs are prepared one micro-batch ahead: after a pipelined loss() the
+            if sub + 1 < f.sub_batch:                                                  # caller's stream is ordered behind that micro-batch's forward pass
+                nxt = fetch(sub + 1)
             loss = model.loss(*tens, dropout_seed=(step * f.sub_batch + sub) * world + rank)
             ave_loss = loss.clone() if ave_loss is None else ave_loss + loss           # ave_loss += loss_value :147 (device add, no sync)
             nf = ~torch.isfinite(loss[0])

@@ -7,6 +7,8 @@ the default suite covers exactly what ships enabled; tools/r2_sweep.py additiona
   DENSEREG_WGRAD_STREAMS=1, DENSEREG_SIDE_STREAM=0   one / no filter-gradient side stream       engine.cu
   DENSEREG_PDL=0, DENSEREG_GRAD_ALIAS=0   no programmatic dependent launch / residual gradients copied instead of aliased   engine.cu
   DENSEREG_BRN_SMALL_ELEMS=0, DENSEREG_EW_REVERSE=0   no one-cluster BRN backward / BRN passes front to back               ew.cu
+  DENSEREG_SPLIT_TRUNC=0      wgrad splitters rewrite hi = rn_tf32(v) as well (default: the landed fp32 tile is the hi operand)     wgrad_tc.cu
+  DENSEREG_PIPELINE=2         micro-batch pipeline forced on for every training engine of the parity suites                     engine.cu
   DENSEREG_WGRAD_SWAP=0, DENSEREG_WGRAD_WAVES=2, DENSEREG_BRN_BLOCKS=1184, DENSEREG_TC_STATS_PER_CTA=0, DENSEREG_POOL_BWD_V4=0   the round-1 settings"""
 import os
 import subprocess
@@ -23,7 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                  {"DENSEREG_LANES": "0"}, {"DENSEREG_WGRAD_STREAMS": "1"}, {"DENSEREG_SIDE_STREAM": "0"},
                                  {"DENSEREG_WGRAD_SWAP": "0", "DENSEREG_WGRAD_WAVES": "2", "DENSEREG_BRN_BLOCKS": "1184", "DENSEREG_TC_STATS_PER_CTA": "0",
                                   "DENSEREG_POOL_BWD_V4": "0"},
-                                 {"DENSEREG_PDL": "0"}, {"DENSEREG_GRAD_ALIAS": "0"}, {"DENSEREG_BRN_SMALL_ELEMS": "0", "DENSEREG_EW_REVERSE": "0"}])
+                                 {"DENSEREG_PDL": "0"}, {"DENSEREG_GRAD_ALIAS": "0"}, {"DENSEREG_BRN_SMALL_ELEMS": "0", "DENSEREG_EW_REVERSE": "0"},
+                                 {"DENSEREG_SPLIT_TRUNC": "0"}, {"DENSEREG_PIPELINE": "2"}])
 def test_parity_suite_with_switch(env):
     e = dict(os.environ, **env)
     e.pop("DENSEREG_TEST_EXPERIMENTAL", None)

@@ -17,6 +17,8 @@ CONFIGS = [   # round-2 sixth pass: programmatic dependent launch
     ("trunc", {"DENSEREG_SPLIT_TRUNC": "1"}),
     ("pipe2_trunc_waves2", {"DENSEREG_PIPELINE": "2", "DENSEREG_SPLIT_TRUNC": "1", "DENSEREG_WGRAD_WAVES": "2"}),
     ("pipe2_waves2", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_WAVES": "2"}),
+    ("pipe2_nopairw", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_PAIR_MINM": "0"}),      # CTA-pair wgrad kernel off / also for 129..255-row layers
+    ("pipe2_pairw_129", {"DENSEREG_PIPELINE": "2", "DENSEREG_WGRAD_PAIR_MINM": "129"}),
     ("no_pdl", {"DENSEREG_PDL": "0"}),
     ("no_grad_alias", {"DENSEREG_GRAD_ALIAS": "0"}),
     ("no_lanes", {"DENSEREG_LANES": "0"}),
