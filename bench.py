@@ -36,7 +36,7 @@ METRICS = {"train": "depth-crops/sec (128x128, 2-stack fea=128) training step", 
            "vote": "depth-crops/sec offset-vote (128x128 maps, J=21)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels named in `roofline`, from the `ncu --set full` captures summarised
 # under profiles/ (r1_final.md: CTA-pair conv on um_comb/c2 at B=40 = 46.8 MB read + 4.3 MB written; r2_*.md for wgrad); None = not captured
-NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": 90.7e6}      # wgrad on um_comb/c2, B=40: 86.3 MB read + 4.4 MB written (profiles/r2_kernels.md)
+NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": None}        # wgrad_tc_pair_kernel on um_comb/c2, B=40: filled from profiles/r2_kernels_pair_wgrad.md once captured
 
 
 def measured_peaks():
@@ -382,18 +382,39 @@ def run_train(args, c):
             eng.loss_backward(d, po, cf, co, dropout_seed=i * SUB + sub)
         eng.optimizer_step(i + 1, 1e-3, accum_steps=SUB, world=world)
 
+    # end to end: every micro-batch's inputs are copied from pinned host memory inside the timed region, ONE micro-batch ahead on a copy
+    # stream into three rotating device staging sets (the usual loader prefetch).  After a pipelined dr_loss_backward the caller's stream is
+    # ordered behind that micro-batch's forward pass and loss, so copies issued on it would start that late and delay the next forward pass.
+    NST = 3
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [[torch.empty_like(t, device=dev) for t in pinned[0]] for _ in range(NST)]
+    ev_ready = [torch.cuda.Event() for _ in range(NST)]
+    ev_consumed = [torch.cuda.Event() for _ in range(NST)]
+    fetched = {"n": -1}
+
+    def prefetch(n):                                  # n = running micro-batch index
+        if n <= fetched["n"]:
+            return
+        fetched["n"] = n
+        j = n % NST
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_consumed[j])    # micro-batch n - 3 has read this set (its loss is computed)
+            for a, b in zip(staging[j], pinned[n % NROT]):
+                a.copy_(b, non_blocking=True)
+            ev_ready[j].record(copy_stream)
+
     def step_e2e(i):
-        # inputs are copied ONE micro-batch ahead (the usual loader prefetch): after a pipelined dr_loss_backward the caller's stream is
-        # ordered behind that micro-batch's forward pass, so a copy issued after the call would start that late
+        cur = torch.cuda.current_stream()
         eng.zero_grads()
-        nxt = [t.to(dev, non_blocking=True) for t in pinned[(i * SUB) % NROT]]
+        prefetch(i * SUB)
         for sub in range(SUB):
-            d, po, cf, co = nxt
-            if sub + 1 < SUB:
-                nxt = [t.to(dev, non_blocking=True) for t in pinned[(i * SUB + sub + 1) % NROT]]
+            n = i * SUB + sub
+            prefetch(n + 1)                           # also across the optimiser step: the copy does not touch parameters or gradients
+            cur.wait_event(ev_ready[n % NST])
             if sub == SUB - 1:
                 eng.comm_overlap_next_backward()
-            loss = eng.loss_backward(d, po, cf, co, dropout_seed=i * SUB + sub)
+            loss = eng.loss_backward(*staging[n % NST], dropout_seed=n)
+            ev_consumed[n % NST].record(cur)          # the call returns with the stream ordered behind this micro-batch's loss kernel
         eng.optimizer_step(i + 1, 1e-3, accum_steps=SUB, world=world)
         loss_host.copy_(loss, non_blocking=True)
 
@@ -405,9 +426,10 @@ def run_train(args, c):
     ar0 = eng.allreduce_count
     ms, launches = timed(c, step_resident, args.warmup, args.steps, eng)
     n_allreduce = eng.allreduce_count - ar0
-    for i in range(max(1, args.warmup // 2)):
+    n_e2e_warm = max(1, args.warmup // 2)
+    for i in range(n_e2e_warm):
         step_e2e(i)
-    ms_e2e, _ = timed(c, step_e2e, args.warmup, args.steps, eng)
+    ms_e2e, _ = timed(c, step_e2e, n_e2e_warm, args.steps, eng)
     clocks = sampler.stop() if rank == 0 else None
     crops = B * SUB * args.steps * world
     value = crops / (ms * 1e-3)
@@ -449,17 +471,28 @@ def run_train(args, c):
     e1.record(); torch.cuda.synchronize()
     w_ms = e0.elapsed_time(e1) / reps
     w_ach = k_flops / (w_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": w_ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": w_ach / peaks["bf16_burst"],
-                "traffic": NCU_TRAFFIC_BYTES["wgrad"] if B == 40 and args.precision == "tf32x3" else None,
-                "kernel": "wgrad_tc_kernel (filter gradient) on its heaviest layer s0/um_comb/c2 3x3 256->256, B=%d, timed alone (includes the memset of the "
-                          "2.4 MB gradient).  wgrad is the TIME-DOMINANT kernel class of the step: %d launches per micro-batch, %.2f ms = %.0f %% of the "
-                          "conv-type time at %.0f TFLOP/s over all its layers (`classes`)"
-                          % (B, top["launches"] if top["class"] == "wgrad" else 0, top["total_ms"], 100.0 * top["total_ms"] / max(traced_ms, 1e-9), top["achieved"]),
-                "kernel_ms": w_ms, "algorithmic_bytes": 4.0 * B * 1024 * 256 * 2 + 4.0 * 9 * 256 * 256,
+    # top-level numbers: the kernel of the TIME-DOMINANT class (conv / dgrad share one kernel) on the heaviest layer of the path, timed alone;
+    # `classes` has every class over all its layers, `other_kernel` the same layer through the other kernel family
+    per_kernel = {
+        "wgrad": {"name": "wgrad_tc_pair_kernel (filter gradient, CTA pairs)", "ms": w_ms, "achieved": w_ach, "traffic": NCU_TRAFFIC_BYTES["wgrad"],
+                  "note": " (includes the memset of the 2.4 MB gradient)"},
+        "conv": {"name": "conv_tc_pair_kernel (implicit-GEMM conv, CTA pairs; dgrad runs the same kernel on rotated weights)", "ms": k_ms, "achieved": best,
+                 "traffic": NCU_TRAFFIC_BYTES["conv"], "note": ""}}
+    dom = "wgrad" if top["class"] == "wgrad" else "conv"
+    oth = "conv" if dom == "wgrad" else "wgrad"
+    pk = per_kernel[dom]
+    roofline = {"bound": "tensor", "achieved": pk["achieved"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": pk["achieved"] / peaks["bf16_burst"],
+                "traffic": pk["traffic"] if B == 40 and args.precision == "tf32x3" else None,
+                "kernel": "%s on the heaviest layer s0/um_comb/c2 3x3 256->256, B=%d, timed alone%s.  %s is the TIME-DOMINANT kernel class of the step: %d "
+                          "launches per micro-batch, %.2f ms = %.0f %% of the conv-type time at %.0f TFLOP/s over all its layers (`classes`)"
+                          % (pk["name"], B, pk["note"], top["class"], top["launches"], top["total_ms"], 100.0 * top["total_ms"] / max(traced_ms, 1e-9), top["achieved"]),
+                "kernel_ms": pk["ms"], "algorithmic_bytes": 4.0 * B * 1024 * 256 * 2 + 4.0 * 9 * 256 * 256,
+                "algorithmic_flops": k_flops,
                 "peak_source": peaks["src"] + " dense bf16 cuBLAS burst (tf32 kind is nominally half of bf16; 3xTF32 issues 3 MMAs per algorithmic MAC: ceiling = peak / 6)",
                 "dominant_class": top["class"], "classes": classes,
-                "best_layer": {"kernel": "conv implicit GEMM (%s, CTA-pair kernel) on s0/um_comb/c2 3x3 256->256, B=%d, timed alone" % (args.precision, B),
-                               "kernel_ms": k_ms, "achieved": best, "frac": best / peaks["bf16_burst"], "traffic": NCU_TRAFFIC_BYTES["conv"] if B == 40 else None},
+                "other_kernel": {"kernel": "%s on the same layer, timed alone%s" % (per_kernel[oth]["name"], per_kernel[oth]["note"]),
+                                 "kernel_ms": per_kernel[oth]["ms"], "achieved": per_kernel[oth]["achieved"], "frac": per_kernel[oth]["achieved"] / peaks["bf16_burst"],
+                                 "traffic": per_kernel[oth]["traffic"] if B == 40 and args.precision == "tf32x3" else None},
                 "whole_step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"], "frac": step_tflops / peaks["bf16_sustained"],
                                "note": "%.2f GFLOP/crop (fwd+dgrad+wgrad conv FLOPs) x crops/s per GPU vs sustained measured peak" % TRAIN_GFLOP_PER_CROP[J]}}
 
