@@ -14,13 +14,14 @@ rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dev = torch.device("cuda", local)
-B, J, SUB = 8, 14, 2
+B, J, SUB = 8, 14, 3
+PIPE = int(os.environ.get("DP_CHECK_PIPELINE", "2"))      # micro-batch pipeline: micro-batches 0 / 2 in the first arena, 1 in the second; the overlapped all-reduce runs in the first
 data = [[torch.from_numpy(a).to(dev) for a in synth.make_batch(B, J, seed=100 * rank + s)] for s in range(SUB)]
-out = {"world": world}
+out = {"world": world, "pipeline": PIPE, "sub_batch": SUB}
 
 
 def run(mode):
-    eng = DenseRegEngine(2, 128, J, max_batch=B, device=local, training=True)
+    eng = DenseRegEngine(2, 128, J, max_batch=B, device=local, training=True, pipeline=PIPE)
     eng.init_params(seed=0)
     if mode != "torch":
         eng.comm_init(rank, world)
@@ -31,6 +32,7 @@ def run(mode):
                 eng.comm_overlap_next_backward()
             eng.loss_backward(*data[s], dropout_seed=step * SUB + s)
         if mode == "torch":
+            eng.join()                                # pipeline: the caller reads the gradient buffer itself
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
         eng.optimizer_step(step + 1, 1e-3, accum_steps=SUB, world=world)
     torch.cuda.synchronize()
