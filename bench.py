@@ -21,6 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context exists: see densereg_b200/__init__.py
 
 # SURVEY.md 8d / BASELINE.md section 2: algorithmic conv FLOPs per crop (2 x MACs of the conv table); training = 3 x forward
 FWD_GFLOP_PER_CROP = {16: 9.790, 14: 9.732, 21: 9.939}
