@@ -36,8 +36,8 @@ CONFIGS = {
 METRICS = {"train": "depth-crops/sec (128x128, 2-stack fea=128) training step", "infer": "depth-crops/sec (128x128, 2-stack fea=128) inference",
            "vote": "depth-crops/sec offset-vote (128x128 maps, J=21)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels named in `roofline`, from the `ncu --set full` captures summarised
-# under profiles/ (r1_final.md: CTA-pair conv on um_comb/c2 at B=40 = 46.8 MB read + 4.3 MB written; r2_*.md for wgrad); None = not captured
-NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": None}        # wgrad_tc_pair_kernel on um_comb/c2, B=40: filled from profiles/r2_kernels_pair_wgrad.md once captured
+# under profiles/ (r1_final.md / r2_kernels.md: CTA-pair conv on um_comb/c2 at B=40 = 46.8 MB read + 4.3 MB written; r2_kernels_pair_wgrad.md: CTA-pair wgrad); None = not captured
+NCU_TRAFFIC_BYTES = {"conv": 51.1e6, "dgrad": 51.1e6, "wgrad": 90.7e6}      # wgrad_tc_pair_kernel on um_comb/c2, B=40: 86.3 MB read + 4.4 MB written (profiles/r2_kernels_pair_wgrad.md)
 
 
 def measured_peaks():
