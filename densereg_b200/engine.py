@@ -48,10 +48,10 @@ class DenseRegEngine:
         kw = dict(dtype=torch.float32, device=self.device)
         self.params = torch.zeros(self.n_params, **kw)
         self.state = torch.zeros(self.n_state, **kw)
-        self.grads = torch.zeros(self.n_params, **kw) if training else None
+        self._grads = torch.zeros(self.n_params, **kw) if training else None
         self.adam_m = torch.zeros(self.n_params, **kw) if training else None
         self.adam_v = torch.zeros(self.n_params, **kw) if training else None
-        self._check(self.lib.dr_bind(self._h, _ptr(self.params), _ptr(self.state), _ptr(self.grads),
+        self._check(self.lib.dr_bind(self._h, _ptr(self.params), _ptr(self.state), _ptr(self._grads),
                                      _ptr(self.adam_m), _ptr(self.adam_v)))
         self.loss_buf = torch.zeros(5, **kw)
 
@@ -208,9 +208,18 @@ class DenseRegEngine:
         return int(self.lib.dr_comm_allreduce_count(self._h))
 
     def join(self):
-        """Micro-batch pipeline (pipeline=2): order the current stream after every backward pass still in flight.  Needed only before
-        reading `self.grads` directly; zero_grads / optimizer_step / forward / infer join by themselves."""
+        """Micro-batch pipeline (pipeline=2): order the current stream after every backward pass still in flight.  zero_grads /
+        optimizer_step / forward / infer join by themselves, and so does the `grads` property; only a caller that kept its own
+        reference to the gradient tensor needs this."""
         self._check(self.lib.dr_pipeline_join(self._h, self._stream()))
+
+    @property
+    def grads(self):
+        """The bound flat gradient buffer (accum_op's accumulators, train_single_gpu.py:69-84), complete on the current stream: with the
+        micro-batch pipeline on, every backward pass still in flight is joined first."""
+        if self._grads is not None and getattr(self, "_h", None) is not None and self._h.value and self.lib.dr_pipeline_depth(self._h) == 2:
+            self.join()
+        return self._grads
 
     @property
     def pipeline_depth(self):
