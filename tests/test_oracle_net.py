@@ -146,3 +146,37 @@ def test_c_abi_error_behaviour_without_a_gpu(built_lib):
     rc = lib.dr_bind(h, fake, fake, None, None, None)
     assert rc == 0 if torch.cuda.is_available() else rc in (0, -2)
     assert lib.dr_destroy(h) == 0
+
+
+def test_pipeline_c_abi_without_a_gpu(built_lib):
+    """Micro-batch pipeline (include/densereg.h, dr_pipeline_join): the second arena is a host-side object until dr_bind, so creation, the
+    depth query, the layer table and destruction are checkable here; the training entry points still refuse without bound gradients."""
+    from densereg_b200 import _ffi
+    lib = built_lib
+    ok = dict(num_stack=1, num_fea=64, kernel_size=3, num_jnt=16, in_hw=128, out_hw=32, max_batch=4, precision=2, device=0)
+    assert lib.dr_pipeline_depth(None) == 0 and lib.dr_pipeline_join(None, None) == -1
+    for want, depth in ((0, 1), (2, 2), (1, 1)):
+        cfg = _ffi.DrConfig(**ok)
+        cfg.reserved[2] = want
+        h = C.c_void_p()
+        assert lib.dr_create(C.byref(h), C.byref(cfg)) == 0 and h.value
+        assert lib.dr_pipeline_depth(h) == depth
+        assert lib.dr_pipeline_join(h, None) == 0                      # nothing in flight: a no-op, no CUDA call
+        assert lib.dr_launch_count(h) == 0 and lib.dr_tc_launch_count(h) == 0
+        n = lib.dr_num_layers(h)
+        assert n > 0 and lib.dr_param_count(h) > 0                     # one parameter set whatever the depth
+        fake = C.c_void_p(0x1000)
+        assert lib.dr_loss_backward(h, 1, fake, fake, fake, fake, fake, 0, 1, None) == -3 and b"grads" in lib.dr_last_error(h)
+        assert lib.dr_zero_grads(h, None) == -3
+        assert lib.dr_destroy(h) == 0
+
+
+def test_import_sets_hardware_queue_default():
+    """densereg_b200/__init__.py: CUDA_DEVICE_MAX_CONNECTIONS defaults to 32 at import (before the CUDA context exists) and a user's value wins."""
+    import subprocess, sys
+    code = "import os; import densereg_b200; print(os.environ['CUDA_DEVICE_MAX_CONNECTIONS'])"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    assert subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True).stdout.strip() == "32"
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "4"
+    assert subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True).stdout.strip() == "4"
