@@ -1,7 +1,8 @@
 """smoke(): small invocations of the hot path on cuda:0, checked against the CPU oracle: forward + vote and one training micro-step on the
 1-stack / 64-feature net, then one training micro-step of the benchmarked configuration (2-stack, 128 features, batch 32) so that the
-tcgen05 kernels bench.py times (one-CTA and CTA-pair conv, tensor-core wgrad) are exercised here too.  Everything runs in the library's
-default arithmetic (3xTF32 on the tensor cores)."""
+tcgen05 kernels bench.py times (one-CTA and CTA-pair conv, one-CTA and CTA-pair wgrad) are exercised here too -- with the micro-batch
+pipeline on, like bench.py: a second micro-batch of the same crops runs in the second arena and must double the accumulated gradient.
+Everything runs in the library's default arithmetic (3xTF32 on the tensor cores)."""
 import numpy as np
 import torch
 
@@ -45,7 +46,7 @@ def run():
     eng.close()
     # ---- the benchmarked configuration: 2-stack fea=128, batch 32 (>= 64 work items per big layer -> CTA-pair kernel)
     S, F, J, B = 2, 128, 16, 32
-    eng = DenseRegEngine(S, F, J, max_batch=B, training=True, precision="tf32x3")
+    eng = DenseRegEngine(S, F, J, max_batch=B, training=True, precision="tf32x3", pipeline=2)
     net = U.Net(S, F, J)
     p, s = net.init_params(0, stddev=0.05), net.init_state()
     eng.load_flat(p, s)
@@ -58,6 +59,13 @@ def run():
     e_loss = abs(loss[0] - L["total"]) / abs(L["total"])
     e_grad = float((eng.grads.cpu() - g_ref).norm() / g_ref.norm())
     n_tc = eng.tc_launch_count - tc0
-    print("smoke: 2x128 B=%d 3xTF32 micro-step: loss relerr %.2e | grad relerr %.2e | tensor-core launches %d of %d"
-          % (B, e_loss, e_grad, n_tc, eng.launch_count))
+    # second micro-batch in the pipeline's second arena: same crops, same dropout seed, BRN state put back to what the first one read (its
+    # update moved d_max from 0 to 1e-3, ops.py:146-149) and not updated again -> the same forward pass, so the accumulated gradient doubles
+    g1 = eng.grads.clone()
+    eng.state.copy_(s.to(eng.device))
+    loss2 = eng.loss_backward(d, po, cf, co, dropout_seed=4, update_state=False).cpu().numpy()
+    e_twin = float((eng.grads - 2.0 * g1).norm() / g1.norm())
+    print("smoke: 2x128 B=%d 3xTF32 micro-step: loss relerr %.2e | grad relerr %.2e | tensor-core launches %d of %d | pipelined second micro-batch: "
+          "grad(2) - 2 grad(1) = %.2e, loss diff %.2e" % (B, e_loss, e_grad, n_tc, eng.launch_count, e_twin, abs(loss2[0] - loss[0]) / abs(loss[0])))
     assert e_loss < 1e-4 and e_grad < 2e-2 and n_tc > 300
+    assert eng.pipeline_depth == 2 and e_twin < 1e-3 and abs(loss2[0] - loss[0]) <= 1e-5 * abs(loss[0])
