@@ -40,6 +40,10 @@ class DrTraceRec(C.Structure):
                 ("kernel", C.c_int32), ("ms", C.c_float)]
 
 
+class DrPipeOp(C.Structure):         # include/densereg.h: dr_pipe_op
+    _fields_ = [("kind", C.c_int32), ("stream", C.c_int32), ("event", C.c_int32)]
+
+
 # every symbol include/densereg.h declares: name -> (restype, argtypes)
 _P, _F, _I32P = C.c_void_p, C.c_void_p, C.c_void_p
 SIGNATURES = {
@@ -62,6 +66,7 @@ SIGNATURES = {
     "dr_loss_backward": (C.c_int, [_P, C.c_int, _F, _F, _F, _F, _F, C.c_uint64, C.c_int, _P]),
     "dr_pipeline_join": (C.c_int, [_P, _P]),
     "dr_pipeline_depth": (C.c_int, [_P]),
+    "dr_debug_pipeline_plan": (C.c_int, [_P, C.c_int, C.POINTER(DrPipeOp), C.c_int]),
     "dr_comm_unique_id": (C.c_int, [_P]),
     "dr_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dr_comm_overlap_next_backward": (C.c_int, [_P]),

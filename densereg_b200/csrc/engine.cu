@@ -156,7 +156,7 @@ struct dr_handle {
   // forward(i+1) after forward(i) (BRN state order = the reference's), backward(i+1) after backward(i) (exclusive gradient accumulation).
   dr_handle* twin = nullptr; bool is_twin = false;
   cudaStream_t pipe_stream[2] = {};
-  cudaEvent_t ev_pipe_in = nullptr, ev_pipe_fwd[2] = {}, ev_pipe_bwd[2] = {}, ev_pipe_loss[2] = {};
+  cudaEvent_t ev_pipe[7] = {};           // indexed by the PE_* ids of the pipeline plan (pipe_plan_micro_batch): in, fwd[2], bwd[2], loss[2]
   int pipe_next = 0; bool pipe_pending = false;
   int64_t pipe_twin_runs = 0;
   // DENSEREG_CHAIN_PRIO=1: the streams of the dependency chain (pipeline streams, lanes > 0) get the greatest stream priority, so that when SMs
@@ -1114,23 +1114,58 @@ int init_device(dr_handle* h) {
 // ---------------------------------------------------------------------------------------------
 int pipe_fail(dr_handle* h, dr_handle* e, int rc) { if (e != h) h->err = e->err; return rc; }
 
-// everything the pipeline still has in flight precedes whatever is enqueued on `st` next (gradients complete, arenas idle)
+// The stream operations of the pipeline as DATA: pipe_loss_backward / pipe_join execute these lists with CUDA calls, dr_debug_pipeline_plan
+// exports the same lists, and tests/test_pipeline_plan.py replays them on a model of CUDA's stream / event semantics (forward passes in
+// order, one backward pass at a time, loss and inputs ordered on the caller's stream, forward(i+1) really free to overlap backward(i)).
+enum { PE_IN = 0, PE_FWD0 = 1, PE_BWD0 = 3, PE_LOSS0 = 5, PE_COUNT = 7 };     // event ids: in, fwd[slot], bwd[slot], loss[slot]
+enum { PS_CALLER = -1 };                                                     // stream ids: the caller's, or the slot's internal stream (0 / 1)
+enum { PO_RECORD = 0, PO_WAIT = 1, PO_FORWARD = 2, PO_BACKWARD = 3 };        // PO_BACKWARD records `event` right after its loss kernels
+struct PipeOp { int kind, stream, event; };
+const int kPipeMaxOps = 12;
+
+// slot of the next micro-batch.  Slot 0 (the handle itself) whenever the pass has to run there: the weight copies must be rebuilt, the pass
+// all-reduces gradient buckets through the handle's communicator, or its launches are being timed one by one
+int pipe_choose_slot(const dr_handle* h, bool* dirty) {
+  *dirty = h->weights_dirty || h->prepped_precision < 0;
+  if (*dirty || h->overlap_armed || h->trace_on || trace_env()) return 0;
+  return h->pipe_next;
+}
+
+int pipe_plan_micro_batch(int k, bool dirty, PipeOp* o) {
+  int n = 0;
+  o[n++] = PipeOp{PO_RECORD, PS_CALLER, PE_IN};              // inputs / zeroed gradients / updated parameters of the caller's stream
+  o[n++] = PipeOp{PO_WAIT, k, PE_IN};
+  if (dirty) o[n++] = PipeOp{PO_WAIT, k, PE_BWD0 + 1};       // a pass still in flight in the second arena reads the weight copies about to be rebuilt
+  o[n++] = PipeOp{PO_WAIT, k, PE_FWD0 + (k ^ 1)};            // BRN moving statistics: forward passes in micro-batch order
+  o[n++] = PipeOp{PO_FORWARD, k, -1};
+  o[n++] = PipeOp{PO_RECORD, k, PE_FWD0 + k};
+  o[n++] = PipeOp{PO_WAIT, k, PE_BWD0 + (k ^ 1)};            // gradient buffer: one backward pass at a time
+  o[n++] = PipeOp{PO_BACKWARD, k, PE_LOSS0 + k};
+  o[n++] = PipeOp{PO_RECORD, k, PE_BWD0 + k};
+  o[n++] = PipeOp{PO_WAIT, PS_CALLER, PE_LOSS0 + k};         // loss_out is valid and the inputs are free on the caller's stream
+  return n;
+}
+
+// everything the pipeline still has in flight precedes whatever is enqueued on the caller's stream next (gradients complete, arenas idle)
+int pipe_plan_join(PipeOp* o) {
+  o[0] = PipeOp{PO_WAIT, PS_CALLER, PE_BWD0};
+  o[1] = PipeOp{PO_WAIT, PS_CALLER, PE_BWD0 + 1};
+  return 2;
+}
+
 int pipe_join(dr_handle* h, cudaStream_t st) {
   if (!h->twin || !h->pipe_pending) return DR_OK;
-  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_pipe_bwd[k], 0));
+  PipeOp ops[kPipeMaxOps];
+  const int n = pipe_plan_join(ops);
+  for (int i = 0; i < n; ++i) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_pipe[ops[i].event], 0));
   h->pipe_pending = false; h->pipe_next = 0;
   return DR_OK;
 }
 
 int pipe_init(dr_handle* h) {
   if (!h->twin || h->pipe_stream[0]) return DR_OK;
-  for (int k = 0; k < 2; ++k) {
-    CUDA_TRY(h, cudaStreamCreateWithPriority(&h->pipe_stream[k], cudaStreamNonBlocking, h->chain_prio));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_fwd[k], cudaEventDisableTiming));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_bwd[k], cudaEventDisableTiming));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_loss[k], cudaEventDisableTiming));
-  }
-  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe_in, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamCreateWithPriority(&h->pipe_stream[k], cudaStreamNonBlocking, h->chain_prio));
+  for (int i = 0; i < PE_COUNT; ++i) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pipe[i], cudaEventDisableTiming));
   return DR_OK;
 }
 
@@ -1145,26 +1180,28 @@ int pipe_loss_backward(dr_handle* h, int B, const float* dm_mm, const float* pos
                        uint64_t dropout_seed, int update_state, cudaStream_t caller) {
   int rc = pipe_init(h);
   if (rc) return rc;
-  // slot 0 (this handle) whenever the pass has to run here: the weight copies must be rebuilt, the pass all-reduces gradient buckets
-  // through this handle's communicator, or its launches are being timed one by one
-  int k = h->pipe_next;
-  const bool dirty = h->weights_dirty || !h->wk;
-  if (dirty || h->overlap_armed || h->trace_on || trace_env()) k = 0;
+  bool dirty = false;
+  const int k = pipe_choose_slot(h, &dirty);
   dr_handle* e = k ? h->twin : h;
-  cudaStream_t es = h->pipe_stream[k];
-  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_in, caller));                  // inputs / zeroed gradients / updated parameters of the caller's stream
-  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_in, 0));
-  if (dirty) CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_bwd[1], 0));  // a twin pass still in flight reads the weight copies about to be rebuilt
-  if (k) { pipe_share_weights(h); ++h->pipe_twin_runs; }
-  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_fwd[k ^ 1], 0));       // BRN moving statistics: forward passes in micro-batch order
-  rc = forward_impl(e, B, dm_mm, coms, 1, update_state, dropout_seed, es);
-  if (rc) return pipe_fail(h, e, rc);
-  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_fwd[k], es));
-  CUDA_TRY(h, cudaStreamWaitEvent(es, h->ev_pipe_bwd[k ^ 1], 0));       // gradient buffer: one backward pass at a time
-  rc = backward_impl(e, B, poses_mm, cfgs, coms, loss_out, es, h->ev_pipe_loss[k]);
-  if (rc) return pipe_fail(h, e, rc);
-  CUDA_TRY(h, cudaEventRecord(h->ev_pipe_bwd[k], es));
-  CUDA_TRY(h, cudaStreamWaitEvent(caller, h->ev_pipe_loss[k], 0));      // loss_out is valid and the inputs are free on the caller's stream
+  PipeOp ops[kPipeMaxOps];
+  const int n = pipe_plan_micro_batch(k, dirty, ops);
+  for (int i = 0; i < n; ++i) {
+    const PipeOp& op = ops[i];
+    cudaStream_t s = op.stream == PS_CALLER ? caller : h->pipe_stream[op.stream];
+    switch (op.kind) {
+      case PO_RECORD: CUDA_TRY(h, cudaEventRecord(h->ev_pipe[op.event], s)); break;
+      case PO_WAIT: CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_pipe[op.event], 0)); break;
+      case PO_FORWARD:
+        if (k) { pipe_share_weights(h); ++h->pipe_twin_runs; }
+        rc = forward_impl(e, B, dm_mm, coms, 1, update_state, dropout_seed, s);
+        if (rc) return pipe_fail(h, e, rc);
+        break;
+      case PO_BACKWARD:
+        rc = backward_impl(e, B, poses_mm, cfgs, coms, loss_out, s, h->ev_pipe[op.event]);
+        if (rc) return pipe_fail(h, e, rc);
+        break;
+    }
+  }
   h->pipe_next = k ^ 1; h->pipe_pending = true;
   return DR_OK;
 }
@@ -1228,13 +1265,8 @@ int dr_destroy(dr_handle* h) {
   if (h->twin) {
     for (int k = 0; k < 2; ++k) if (h->pipe_stream[k]) cudaStreamSynchronize(h->pipe_stream[k]);
     dr_destroy(h->twin); h->twin = nullptr;
-    for (int k = 0; k < 2; ++k) {
-      if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
-      if (h->ev_pipe_fwd[k]) cudaEventDestroy(h->ev_pipe_fwd[k]);
-      if (h->ev_pipe_bwd[k]) cudaEventDestroy(h->ev_pipe_bwd[k]);
-      if (h->ev_pipe_loss[k]) cudaEventDestroy(h->ev_pipe_loss[k]);
-    }
-    if (h->ev_pipe_in) cudaEventDestroy(h->ev_pipe_in);
+    for (int k = 0; k < 2; ++k) if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
+    for (cudaEvent_t ev : h->ev_pipe) if (ev) cudaEventDestroy(ev);
   }
   if (h->is_twin) h->wk = h->wa = h->wk_hi = h->wk_lo = h->wa_hi = h->wa_lo = nullptr;     // owned by the first handle
   if (h->nccl_comm) { nccl_api().comm_destroy(h->nccl_comm); h->nccl_comm = nullptr; }
@@ -1483,6 +1515,33 @@ int dr_pipeline_join(dr_handle* h, void* stream) {
 }
 
 int dr_pipeline_depth(const dr_handle* h) { return h ? (h->twin ? 2 : 1) : 0; }
+
+int dr_debug_pipeline_plan(dr_handle* h, int what, dr_pipe_op* out, int cap) {
+  if (!h || !out || cap < kPipeMaxOps || what < 0 || what > 3) return DR_ERR_ARG;
+  if (!h->twin) return fail(h, DR_ERR_STATE, "dr_debug_pipeline_plan: the handle has no micro-batch pipeline (dr_config.reserved[2] != 2)");
+  if (h->params) return fail(h, DR_ERR_STATE, "dr_debug_pipeline_plan is a dry run: only on a handle that was never bound");
+  PipeOp ops[kPipeMaxOps];
+  int n = 0;
+  switch (what) {
+    case 0: {                                    // the next dr_loss_backward, with the bookkeeping the real call (and the passes it runs) would do
+      bool dirty = false;
+      const int k = pipe_choose_slot(h, &dirty);
+      n = pipe_plan_micro_batch(k, dirty, ops);
+      h->weights_dirty = false; h->prepped_precision = h->precision;       // ensure_prepped() in the forward pass
+      h->overlap_armed = false;                                            // consumed by the backward pass
+      h->pipe_next = k ^ 1; h->pipe_pending = true;
+      break;
+    }
+    case 1: case 2:                              // dr_pipeline_join / dr_zero_grads (1), dr_optimizer_step (2): join, (2) parameters changed
+      if (h->pipe_pending) n = pipe_plan_join(ops);
+      h->pipe_pending = false; h->pipe_next = 0;
+      if (what == 2) h->weights_dirty = true;
+      break;
+    case 3: h->overlap_armed = true; break;      // dr_comm_overlap_next_backward with a communicator
+  }
+  for (int i = 0; i < n; ++i) { out[i].kind = ops[i].kind; out[i].stream = ops[i].stream; out[i].event = ops[i].event; }
+  return n;
+}
 
 int dr_comm_unique_id(void* out128) {
   if (!out128) return DR_ERR_ARG;

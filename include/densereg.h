@@ -146,6 +146,14 @@ DR_API int dr_loss_backward(dr_handle* h, int B, const float* dm_mm, const float
  * buffer directly calls dr_pipeline_join(h, stream) first.  dr_pipeline_depth: 1 (off) or 2. */
 DR_API int dr_pipeline_join(dr_handle* h, void* stream);
 DR_API int dr_pipeline_depth(const dr_handle* h);
+/* Debug / CPU test (tests/test_pipeline_plan.py): the pipeline's stream operations as data -- the very lists dr_loss_backward / dr_pipeline_join
+ * execute.  Dry run on a handle that was never bound (no CUDA call): what = 0 the next dr_loss_backward (advances the slot bookkeeping like the real
+ * call), 1 dr_pipeline_join / dr_zero_grads, 2 dr_optimizer_step (join + parameters changed), 3 dr_comm_overlap_next_backward (arms the next pass).
+ * kind: 0 record `event` on `stream`, 1 `stream` waits for `event`, 2 forward pass on `stream`, 3 backward pass on `stream` (records `event` right after
+ * its loss kernels); stream: -1 the caller's, 0 / 1 the slot's internal stream; event: 0 in, 1 / 2 forward done [slot], 3 / 4 backward done [slot],
+ * 5 / 6 loss done [slot].  Returns the number of ops written (cap >= 12) or a negative status. */
+typedef struct dr_pipe_op { int32_t kind, stream, event; } dr_pipe_op;
+DR_API int dr_debug_pipeline_plan(dr_handle* h, int what, dr_pipe_op* out, int cap);
 
 /* Data-parallel communicator: replaces model/train_multi_gpu.py:16-39 (_average_gradients: per-variable concat + mean through host
  * memory) and :63-64,73-92 (towers) with one process per GPU and ONE NCCL all-reduce(sum) of the flat gradient per optimiser step.
