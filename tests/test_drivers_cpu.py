@@ -86,6 +86,11 @@ def test_train_loop_sharding_logs_and_checkpoints(fake, monkeypatch):
     opts = [c for c in eng.calls if c[0] == "opt"]
     assert opts[0][1:] == (1, 1e-3, 2, 2) and opts[-1][1] == 101
     assert len(reduced) == 101 and reduced[0] == (2.0, 2)                 # ONE all-reduce per optimiser step, after both micro-batches
+    # micro-batch pipeline: the host-side collective reads the gradient buffer itself, so the pipeline is joined first -- once per step,
+    # after the last loss() and before the optimiser step
+    joins = [i for i, c in enumerate(eng.calls) if c[0] == "join"]
+    assert len(joins) == 101 and all(eng.calls[i - 1][0] == "loss" and eng.calls[i + 1][0] == "opt" for i in joins)
+    assert model.flags.pipeline == 2                                      # default of the training driver
     assert not os.path.exists(model.train_dir) and logs == []             # only rank 0 logs / saves
     # rank 0, single process: logs every 5 steps, validation every 40, checkpoint at step 100 in BOTH formats
     M.train(model, rank=0, world=1, log=logs.append)
